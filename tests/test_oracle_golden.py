@@ -1,0 +1,77 @@
+"""Pins oracle/segpath_oracle.c against vectors produced by the reference's own code
+(tests/golden/make_golden.py).  CPU only."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+
+DT = {"float32": 0, "bfloat16": 1, "float16": 2}
+
+
+def _up_bits(up_f32, dtype):
+    """fp32 array holding dtype-rounded values -> the bit pattern torch stores for that dtype."""
+    if dtype == "float32":
+        return up_f32
+    if dtype == "float16":
+        return up_f32.astype(np.float16).view(np.uint16)
+    return (up_f32.view(np.uint32) >> 16).astype(np.uint16)      # exact: values are already bf16
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_upsample_bits(oracle, name):
+    g = load_golden(name)
+    up = oracle.upsample(g["logits"], tuple(g["size"]), DT[g["logits_dtype"]])
+    got = _up_bits(up, g["logits_dtype"])
+    assert hashlib.sha256(np.ascontiguousarray(got).tobytes()).hexdigest() == str(g["up_sha256"])
+    if "up" in g:
+        assert np.array_equal(got.view(np.uint8), g["up"].view(np.uint8))
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_argmax_and_hist_exact(oracle, name):
+    g = load_golden(name)
+    f = oracle.path_forward(g["logits"], g["labels"], 255, g["class_w"], oracle.OHEM_THRESH, DT[g["logits_dtype"]])
+    assert np.array_equal(f["arg_px"].reshape(g["argmax"].shape), g["argmax"].astype(np.int32))
+    assert np.array_equal(f["hist"], g["mat_i64"])
+    assert np.array_equal(f["hist"].astype(np.float32), g["hist_f32"])
+    assert int(f["sums"][2]) == int(g["n_valid"])
+    # ConfusionMatrix.update twin (utils.py:99-109)
+    mat = oracle.hist_pairs(g["labels"].reshape(-1).astype(np.int64), g["argmax"].reshape(-1).astype(np.int64),
+                            g["logits"].shape[1])
+    assert np.array_equal(mat, g["mat_i64"])
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_loss_px_and_scalar(oracle, name):
+    g = load_golden(name)
+    dt = DT[g["logits_dtype"]]
+    f = oracle.path_forward(g["logits"], g["labels"], 255, g["class_w"], oracle.OHEM_THRESH, dt,
+                            want_arg=False, want_hist=False)
+    np.testing.assert_allclose(f["loss_px"].reshape(g["loss_px"].shape), g["loss_px"], rtol=2e-6, atol=2e-6)
+    if g["loss_kind"] == "ce":
+        loss, _ = oracle.ce_loss_and_grad(g["logits"], g["labels"], 255, g["class_w"], dt, want_grad=False)
+    else:
+        loss, _, info = oracle.ohem_loss_and_grad(g["logits"], g["labels"], 255, g["class_w"], ldtype=dt, want_grad=False)
+        assert abs(info["n_hard"] - int(g["n_hard"])) <= 2          # pixels within an ulp of the threshold
+        assert info["branch"] == int(int(g["n_hard"]) < int(g["n_valid"]) // 16)
+    if np.isnan(g["loss"]):
+        assert np.isnan(loss)                                       # all-ignored batch
+    else:
+        assert abs(loss - float(g["loss"])) <= 1e-6 * abs(float(g["loss"])) + 1e-7
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if "all_ignored" not in n])
+def test_gradient(oracle, name):
+    g = load_golden(name)
+    dt = DT[g["logits_dtype"]]
+    if g["loss_kind"] == "ce":
+        _, grad = oracle.ce_loss_and_grad(g["logits"], g["labels"], 255, g["class_w"], dt)
+    else:
+        _, grad, _ = oracle.ohem_loss_and_grad(g["logits"], g["labels"], 255, g["class_w"], ldtype=dt)
+    ref = g["grad"]
+    scale = np.abs(ref).max()
+    # fp32 reference grads carry fp32 accumulation noise; low-precision ones were rounded to bf16/fp16
+    tol = 1e-5 if g["logits_dtype"] == "float32" else 1e-2
+    assert np.abs(grad - ref).max() <= tol * scale, (np.abs(grad - ref).max(), scale)
