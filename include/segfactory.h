@@ -1,0 +1,122 @@
+/*
+ * segfactory.h -- C ABI of libsegfactory.so (sm_100a).
+ *
+ * The reference (jiaowoguanren0615/Segmentation_Factory) has no FFI for this path: the per-pixel
+ * head-to-metric work is a chain of PyTorch ATen calls made from Python.  Each entry point below
+ * replaces one such chain; the Python mirror of the reference API (segmentation_factory_b200/)
+ * binds them with ctypes.  INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless it says "host"; the caller owns all memory, the
+ *     library allocates nothing and keeps no mutable global state (re-entrant, any host thread);
+ *   - `stream` is a cudaStream_t passed as void*; nothing here synchronises with the host;
+ *   - tensors are dense: logits [B,C,h,w] (NCHW), labels [B,H,W]; H,W may differ from h,w, the
+ *     bilinear upsample (align_corners=False) of models/build_models.py:65 happens in-kernel;
+ *   - return 0 on success, a negative sf_status, or a positive cudaError_t from the launch;
+ *   - labels equal to `ignore`, negative, or >= C take no part in loss, gradient or histogram.
+ */
+#ifndef SEGFACTORY_H_
+#define SEGFACTORY_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SF_VERSION 100            /* 0.1.0 */
+
+enum sf_dtype       { SF_F32 = 0, SF_BF16 = 1, SF_F16 = 2 };     /* logits / gradient element type */
+enum sf_label_dtype { SF_I64 = 0, SF_U8 = 1 };                   /* datasets/*.py: int64, Kvasir uint8 */
+
+enum sf_status {
+    SF_OK              =  0,
+    SF_ERR_ARG         = -1,     /* null pointer, non-positive extent, unknown dtype           */
+    SF_ERR_ALIGN       = -2,     /* a pointer is not aligned to its element size               */
+    SF_ERR_TOO_MANY_CLASSES = -3,/* C*C int32 histogram does not fit in shared memory (C > 230) */
+    SF_ERR_WORKSPACE   = -4,     /* workspace smaller than sf_workspace_bytes()                */
+    SF_ERR_DRIVER      = -5,     /* cuTensorMapEncodeTiled unavailable / failed                */
+    SF_ERR_SHAPE       = -6      /* extents overflow the kernels' 32-bit tile arithmetic       */
+};
+
+/* Device-resident result of sf_loss_finalize (first bytes of the workspace). */
+typedef struct sf_loss_state {
+    float    loss;        /* the scalar the reference's forward() returns                       */
+    float    kth;         /* pixels with loss_px >  kth are kept with weight 1                  */
+    float    tie_share;   /* pixels with loss_px == kth are kept with this weight (top-k ties)  */
+    float    inv_denom;   /* 1/K (OHEM) or 1/sum(w_y) (CE): d loss / d loss_px of a kept pixel  */
+    int32_t  branch;      /* 0 = CE, 1 = OHEM threshold branch, 2 = OHEM top-k branch           */
+    int32_t  reserved;
+    uint64_t n_valid;     /* non-ignored pixels                                                 */
+    uint64_t n_hard;      /* pixels with loss_px > thresh                                       */
+    uint64_t n_kept;      /* K                                                                  */
+    double   sum_kept;    /* sum of kept per-pixel losses                                       */
+    double   sum_w;       /* sum of class weights over valid pixels                             */
+} sf_loss_state;
+
+int         sf_version(void);
+const char* sf_strerror(int code);
+
+/* Bytes of zero-initialised-once device scratch sf_ce_forward / sf_loss_finalize / sf_ce_backward share. */
+size_t sf_workspace_bytes(void);
+
+/*
+ * Replaces engine.py:90-91 -- outputs.argmax(1) twice + Metrics.update (util/metrics.py:24-27) +
+ * ConfusionMatrix.update (util/utils.py:99-109) -- and the upsample feeding them.
+ * hist[C*C] (rows = ground truth, cols = prediction) is ACCUMULATED into.
+ */
+int sf_eval_hist(const void* logits, int ldtype, const void* labels, int ydtype,
+                 int B, int C, int h, int w, int H, int W, int ignore,
+                 unsigned long long* hist, void* stream);
+
+/*
+ * Replaces F.interpolate + nn.CrossEntropyLoss(weight, ignore_index, reduction='none')
+ * (util/losses.py:32,50,55) and, when hist != NULL, the argmax/bincount of Metrics.update.
+ *   class_w   [C] fp32 or NULL
+ *   ohem_thresh  -log(0.7) style threshold; pass a negative value for plain CrossEntropy
+ *   loss_px   [B*H*W] fp32, w_y*(lse - z_y), 0 where ignored   (NULL allowed for plain CE)
+ *   lse_px    [B*H*W] fp32 log-sum-exp, consumed by sf_ce_backward (NULL when no gradient is needed)
+ *   hist      [C*C] accumulated (NULL to skip the argmax/histogram)
+ *   workspace >= sf_workspace_bytes(); per-CTA partial sums are left there for sf_loss_finalize
+ */
+int sf_ce_forward(const void* logits, int ldtype, const void* labels, int ydtype,
+                  int B, int C, int h, int w, int H, int W, int ignore,
+                  const float* class_w, float ohem_thresh,
+                  float* loss_px, float* lse_px, unsigned long long* hist,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Replaces the reductions of util/losses.py:36 (weighted mean) and :54-61 (n_min, threshold test,
+ * topk fallback, mean) without host synchronisation.  Reads the partial sums sf_ce_forward left in
+ * `workspace`; if fewer than n_valid/16 pixels exceed ohem_thresh it radix-selects the n_min-th
+ * largest loss from loss_px.  Writes sf_loss_state at workspace[0] and, when loss_out != NULL, the
+ * scalar loss to *loss_out (device fp32) so the caller can hand it to autograd without a copy.
+ */
+int sf_loss_finalize(const float* loss_px, long long n_px, float ohem_thresh,
+                     void* workspace, size_t workspace_bytes, float* loss_out, void* stream);
+
+/*
+ * Replaces autograd's nll_loss2d_backward + _log_softmax_backward_data + upsample_bilinear2d_backward.
+ * Gather-form: every low-res gradient element is produced by exactly one CTA, no global atomics.
+ *   grad_out     device fp32 scalar (d L / d loss, e.g. the GradScaler's scale) or NULL for 1.0
+ *   grad_logits  [B,C,h,w] in the logits' dtype, overwritten
+ */
+int sf_ce_backward(const void* logits, int ldtype, const void* labels, int ydtype,
+                   int B, int C, int h, int w, int H, int W, int ignore,
+                   const float* class_w, const float* loss_px, const float* lse_px,
+                   const float* grad_out, const void* workspace,
+                   void* grad_logits, void* stream);
+
+/*
+ * Replaces ConfusionMatrix.update(a, b) (util/utils.py:99-109) when the caller already holds the
+ * flattened label / prediction index vectors (the unmodified engine.py:90 call).
+ *   a [n] labels (int64 or uint8), b [n] int64 predictions in [0,C); mat[C*C] accumulated.
+ */
+int sf_hist_pairs(const void* a, int adtype, const long long* b, long long n, int C,
+                  unsigned long long* mat, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEGFACTORY_H_ */

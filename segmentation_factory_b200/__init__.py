@@ -1,0 +1,15 @@
+"""segmentation_factory_b200 -- B200-native per-pixel head-to-metric path of Segmentation_Factory.
+
+Mirrors the reference's util/ API for this path only:
+    CrossEntropy, OhemCrossEntropy, get_loss        (util/losses.py)
+    Metrics                                         (util/metrics.py)
+    ConfusionMatrix                                 (util/utils.py)
+backed by hand-written sm_100a kernels in libsegfactory.so (C ABI: include/segfactory.h).
+"""
+from .losses import CrossEntropy, OhemCrossEntropy, get_loss
+from .metrics import ConfusionMatrix, Metrics, fused_eval_update
+from .functional import eval_hist, fused_cross_entropy, hist_pairs
+
+__all__ = ["CrossEntropy", "OhemCrossEntropy", "get_loss", "Metrics", "ConfusionMatrix",
+           "fused_eval_update", "fused_cross_entropy", "eval_hist", "hist_pairs"]
+__version__ = "0.1.0"

@@ -1,0 +1,129 @@
+// sf_api.cu -- the extern "C" surface declared in include/segfactory.h, plus the TMA descriptor helper.
+#include <cstdlib>
+#include <cstring>
+
+#include "sf_common.cuh"
+#include "sf_launch.h"
+
+namespace sf {
+
+int sm_count() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+    return n;
+}
+
+bool env_no_tma() {
+    const char* e = std::getenv("SF_NO_TMA");
+    return e && e[0] == '1';
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// libcuda is not linked: the encoder is fetched through the runtime (no -lcuda, works with any driver >= 12.0)
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+        if (q != cudaDriverEntryPointSuccess) return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+int make_logits_tmap(CUtensorMap* map, const void* logits, int ldtype, int planes, int h, int w,
+                     int box_c, int box_h, int box_w) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return SF_ERR_DRIVER;
+    const cuuint64_t esz = ldtype == SF_F32 ? 4 : 2;
+    const CUtensorMapDataType dt = ldtype == SF_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : ldtype == SF_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                     : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    const cuuint64_t gdim[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)planes};
+    const cuuint64_t gstr[2] = {(cuuint64_t)w * esz, (cuuint64_t)w * h * esz};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_c};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(map, dt, 3, const_cast<void*>(logits), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : SF_ERR_DRIVER;
+}
+
+}  // namespace sf
+
+extern "C" {
+
+int sf_version(void) { return SF_VERSION; }
+
+const char* sf_strerror(int code) {
+    switch (code) {
+        case SF_OK: return "ok";
+        case SF_ERR_ARG: return "invalid argument (null pointer, non-positive extent or unknown dtype)";
+        case SF_ERR_ALIGN: return "pointer not aligned to its element size";
+        case SF_ERR_TOO_MANY_CLASSES: return "C*C int32 histogram does not fit in shared memory";
+        case SF_ERR_WORKSPACE: return "workspace smaller than sf_workspace_bytes()";
+        case SF_ERR_DRIVER: return "cuTensorMapEncodeTiled unavailable or failed";
+        case SF_ERR_SHAPE: return "extents overflow the kernels' tile arithmetic";
+        default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "unknown segfactory error";
+    }
+}
+
+size_t sf_workspace_bytes(void) { return sizeof(sf::Workspace); }
+
+int sf_eval_hist(const void* logits, int ldtype, const void* labels, int ydtype, int B, int C, int h, int w, int H,
+                 int W, int ignore, unsigned long long* hist, void* stream) {
+    if (!hist) return SF_ERR_ARG;
+    sf::FwdArgs a{};
+    a.logits = logits; a.ldtype = ldtype; a.labels = labels; a.ydtype = ydtype;
+    a.B = B; a.C = C; a.h = h; a.w = w; a.H = H; a.W = W; a.ignore = ignore;
+    a.hist = hist; a.stream = stream; a.softmax = false; a.force_no_tma = sf::env_no_tma();
+    return sf::launch_forward(a);
+}
+
+int sf_ce_forward(const void* logits, int ldtype, const void* labels, int ydtype, int B, int C, int h, int w, int H,
+                  int W, int ignore, const float* class_w, float ohem_thresh, float* loss_px, float* lse_px,
+                  unsigned long long* hist, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!workspace) return SF_ERR_ARG;
+    if (workspace_bytes < sizeof(sf::Workspace)) return SF_ERR_WORKSPACE;
+    if (ohem_thresh >= 0.f && !loss_px) return SF_ERR_ARG;          // the top-k fallback needs the loss vector
+    sf::FwdArgs a{};
+    a.logits = logits; a.ldtype = ldtype; a.labels = labels; a.ydtype = ydtype;
+    a.B = B; a.C = C; a.h = h; a.w = w; a.H = H; a.W = W; a.ignore = ignore;
+    a.class_w = class_w; a.thresh = ohem_thresh; a.loss_px = loss_px; a.lse_px = lse_px;
+    a.hist = hist; a.ws = workspace; a.stream = stream; a.softmax = true; a.force_no_tma = sf::env_no_tma();
+    return sf::launch_forward(a);
+}
+
+int sf_loss_finalize(const float* loss_px, long long n_px, float ohem_thresh, void* workspace, size_t workspace_bytes,
+                     float* loss_out, void* stream) {
+    if (!workspace || n_px <= 0) return SF_ERR_ARG;
+    if (workspace_bytes < sizeof(sf::Workspace)) return SF_ERR_WORKSPACE;
+    if (ohem_thresh >= 0.f && !loss_px) return SF_ERR_ARG;
+    return sf::launch_finalize(loss_px, n_px, ohem_thresh, workspace, loss_out, stream);
+}
+
+int sf_ce_backward(const void* logits, int ldtype, const void* labels, int ydtype, int B, int C, int h, int w, int H,
+                   int W, int ignore, const float* class_w, const float* loss_px, const float* lse_px,
+                   const float* grad_out, const void* workspace, void* grad_logits, void* stream) {
+    if (!workspace || !grad_logits || !lse_px) return SF_ERR_ARG;
+    sf::BwdArgs a{};
+    a.logits = logits; a.ldtype = ldtype; a.labels = labels; a.ydtype = ydtype;
+    a.B = B; a.C = C; a.h = h; a.w = w; a.H = H; a.W = W; a.ignore = ignore;
+    a.class_w = class_w; a.loss_px = loss_px; a.lse_px = lse_px; a.grad_out = grad_out; a.ws = workspace;
+    a.grad_logits = grad_logits; a.stream = stream; a.force_no_tma = sf::env_no_tma();
+    return sf::launch_backward(a);
+}
+
+int sf_hist_pairs(const void* a, int adtype, const long long* b, long long n, int C, unsigned long long* mat,
+                  void* stream) {
+    if (!a || !b || !mat || n < 0 || C <= 0) return SF_ERR_ARG;
+    if (adtype < SF_I64 || adtype > SF_U8) return SF_ERR_ARG;
+    if (n == 0) return SF_OK;
+    return sf::launch_hist_pairs(a, adtype, b, n, C, mat, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,50 @@
+// sf_launch.h -- host-side launcher interfaces shared by the translation units of libsegfactory.so.
+#pragma once
+
+#include <cuda.h>
+#include <stddef.h>
+
+#include <algorithm>
+
+namespace sf {
+
+struct FwdArgs {
+    const void* logits; int ldtype;
+    const void* labels; int ydtype;
+    int B, C, h, w, H, W, ignore;
+    const float* class_w;
+    float thresh;
+    float* loss_px; float* lse_px;
+    unsigned long long* hist;
+    void* ws;
+    void* stream;
+    bool softmax;          // false: argmax + histogram only (sf_eval_hist)
+    bool force_no_tma;     // SF_NO_TMA=1 in the environment (debug / A-B measurement)
+};
+int launch_forward(const FwdArgs& a);
+
+struct BwdArgs {
+    const void* logits; int ldtype;
+    const void* labels; int ydtype;
+    int B, C, h, w, H, W, ignore;
+    const float* class_w;
+    const float* loss_px; const float* lse_px;
+    const float* grad_out;
+    const void* ws;
+    void* grad_logits;
+    void* stream;
+    bool force_no_tma;
+};
+int launch_backward(const BwdArgs& a);
+
+int launch_finalize(const float* loss_px, long long n_px, float thresh, void* ws, float* loss_out, void* stream);
+int launch_hist_pairs(const void* a, int adtype, const long long* b, long long n, int C,
+                      unsigned long long* mat, void* stream);
+
+// 3-D tiled tensor map over logits viewed as [planes = B*C][h][w]; box = [box_c][box_h][box_w]
+int make_logits_tmap(CUtensorMap* map, const void* logits, int ldtype, int planes, int h, int w,
+                     int box_c, int box_h, int box_w);
+int sm_count();
+bool env_no_tma();
+
+}  // namespace sf

@@ -1,0 +1,194 @@
+// sf_select.cu -- loss reduction + OHEM k-th-largest radix select, entirely on device.
+//
+// Replaces util/losses.py:36 (weighted mean) and util/losses.py:54-61:
+//     n_min = labels[labels != ignore].numel() // 16          (host sync in the reference)
+//     loss_hard = loss[loss > thresh]                          (host sync)
+//     if loss_hard.numel() < n_min: loss_hard, _ = loss.topk(n_min)   (python branch on a device count)
+//     return mean(loss_hard)
+// One cooperative launch: every CTA reduces the per-CTA partial sums sf_ce_forward left in the workspace
+// (fixed order -> identical decision in every CTA, bitwise reproducible loss).  Only when fewer than n_min
+// pixels exceed the threshold does the grid continue into a 3-pass (11+11+10 bit) radix select of the
+// n_min-th largest per-pixel loss over order-preserving uint32 keys, plus one pass summing the losses
+// above it.  Ties at the k-th value share the remaining slots equally (tie_share); torch.topk breaks
+// them arbitrarily, the loss value is identical either way.
+#include <cooperative_groups.h>
+
+#include "sf_common.cuh"
+#include "sf_launch.h"
+
+namespace cg = cooperative_groups;
+
+namespace sf {
+
+constexpr int kSelThreads = 512;
+
+__device__ __forceinline__ unsigned key_of(float v) {           // total order: -NaN < -inf < ... < +inf < +NaN
+    const unsigned u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float val_of(unsigned key) {
+    return __uint_as_float((key & 0x80000000u) ? (key & 0x7fffffffu) : ~key);
+}
+
+struct BinPick { unsigned bin; unsigned long long k_rem; unsigned long long cnt; };
+
+// Find the bin holding the k-th largest key (bins scanned from the top).  All threads must call.
+__device__ BinPick pick_bin(const unsigned* hist, int nbins, unsigned long long k,
+                            unsigned long long* warp_tot, BinPick* out) {
+    const int per = nbins / kSelThreads;                          // 4 (2048 bins) or 2 (1024 bins)
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    unsigned long long c = 0;
+    for (int q = 0; q < per; ++q) c += __ldcg(hist + (nbins - 1 - (t * per + q)));   // written by atomics this launch
+    unsigned long long incl = c;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    unsigned long long base = 0;
+    for (int w = 0; w < warp; ++w) base += warp_tot[w];
+    const unsigned long long excl = base + incl - c;
+    if (excl < k && k <= excl + c) {
+        unsigned long long cum = excl;
+        for (int q = 0; q < per; ++q) {
+            const int b = nbins - 1 - (t * per + q);
+            const unsigned long long h = __ldcg(hist + b);
+            if (k <= cum + h) { out->bin = (unsigned)b; out->k_rem = k - cum; out->cnt = h; break; }
+            cum += h;
+        }
+    }
+    __syncthreads();
+    return *out;
+}
+
+template <int SHIFT, int NBINS, int PREFIX_SHIFT>
+__device__ void radix_pass(const float* __restrict__ v, long long n, unsigned prefix, unsigned* sh, unsigned* gh) {
+    for (int b = threadIdx.x; b < NBINS; b += kSelThreads) sh[b] = 0;
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * kSelThreads;
+    const long long gtid = (long long)blockIdx.x * kSelThreads + threadIdx.x;
+    auto add = [&](float x) {
+        const unsigned key = key_of(x);
+        if (PREFIX_SHIFT >= 32 || (key >> (PREFIX_SHIFT & 31)) == prefix) atomicAdd(&sh[(key >> SHIFT) & (NBINS - 1)], 1u);
+    };
+    if ((reinterpret_cast<uintptr_t>(v) & 15) == 0) {
+        const long long n4 = n >> 2;
+        const float4* v4 = reinterpret_cast<const float4*>(v);
+        for (long long i = gtid; i < n4; i += stride) {
+            const float4 q = __ldg(v4 + i);
+            add(q.x); add(q.y); add(q.z); add(q.w);
+        }
+        for (long long i = (n4 << 2) + gtid; i < n; i += stride) add(__ldg(v + i));
+    } else {
+        for (long long i = gtid; i < n; i += stride) add(__ldg(v + i));
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < NBINS; b += kSelThreads)
+        if (sh[b]) atomicAdd(&gh[b], sh[b]);
+}
+
+__global__ void __launch_bounds__(kSelThreads, 1)
+finalize_kernel(const float* __restrict__ loss_px, long long n, float thresh, Workspace* ws, float* loss_out) {
+    __shared__ double red[kSelThreads / 32];
+    __shared__ double tot[5];
+    __shared__ unsigned sh_hist[kRadixBins];
+    __shared__ unsigned long long warp_tot[kSelThreads / 32];
+    __shared__ BinPick pick;
+
+    // ---- phase 0: fixed-order reduction of the forward kernel's per-CTA partials ----
+    const int np = (int)ws->n_partials;
+    for (int f = 0; f < 5; ++f) {
+        double a = 0.0;
+        for (int i = threadIdx.x; i < np; i += kSelThreads) a += ws->partials[i][f];
+        const double r = block_sum<kSelThreads>(a, red);
+        if (threadIdx.x == 0) tot[f] = r;
+    }
+    __syncthreads();
+    const double sum_loss = tot[0], sum_w = tot[1], sum_hard = tot[2];
+    const unsigned long long n_valid = (unsigned long long)tot[3], n_hard = (unsigned long long)tot[4];
+    const bool writer = blockIdx.x == 0 && threadIdx.x == 0;
+    sf_loss_state st;
+    st.reserved = 0; st.n_valid = n_valid; st.n_hard = n_hard; st.sum_w = sum_w; st.tie_share = 0.f;
+
+    if (thresh < 0.f) {                                             // CrossEntropy: sum(w_y l) / sum(w_y)
+        if (writer) {
+            st.loss = (float)(sum_loss / sum_w); st.kth = -INFINITY; st.inv_denom = (float)(1.0 / sum_w);
+            st.branch = 0; st.n_kept = n_valid; st.sum_kept = sum_loss;
+            ws->state = st;
+            if (loss_out) *loss_out = st.loss;
+        }
+        return;
+    }
+    const unsigned long long n_min = n_valid / 16;
+    if (n_hard >= n_min) {                                          // threshold branch (mean of empty = NaN)
+        if (writer) {
+            st.loss = (float)(sum_hard / (double)n_hard); st.kth = thresh; st.inv_denom = (float)(1.0 / (double)n_hard);
+            st.branch = 1; st.n_kept = n_hard; st.sum_kept = sum_hard;
+            ws->state = st;
+            if (loss_out) *loss_out = st.loss;
+        }
+        return;
+    }
+
+    // ---- top-k branch: k = n_min >= 1 ----
+    cg::grid_group grid = cg::this_grid();
+    const unsigned long long k = n_min;
+    {
+        unsigned* rh = &ws->radix_hist[0][0];
+        for (long long i = (long long)blockIdx.x * kSelThreads + threadIdx.x; i < 3 * kRadixBins;
+             i += (long long)gridDim.x * kSelThreads) rh[i] = 0;
+    }
+    grid.sync();
+    radix_pass<21, 2048, 32>(loss_px, n, 0u, sh_hist, ws->radix_hist[0]);
+    grid.sync();
+    const BinPick p1 = pick_bin(ws->radix_hist[0], 2048, k, warp_tot, &pick);
+    radix_pass<10, 2048, 21>(loss_px, n, p1.bin, sh_hist, ws->radix_hist[1]);
+    grid.sync();
+    const BinPick p2 = pick_bin(ws->radix_hist[1], 2048, p1.k_rem, warp_tot, &pick);
+    const unsigned prefix22 = (p1.bin << 11) | p2.bin;
+    radix_pass<0, 1024, 10>(loss_px, n, prefix22, sh_hist, ws->radix_hist[2]);
+    grid.sync();
+    const BinPick p3 = pick_bin(ws->radix_hist[2], 1024, p2.k_rem, warp_tot, &pick);
+    const unsigned kth_key = (prefix22 << 10) | p3.bin;
+    const float kth = val_of(kth_key);
+
+    // ---- sum of the losses strictly above the k-th value ----
+    double a = 0.0;
+    {
+        const long long stride = (long long)gridDim.x * kSelThreads;
+        for (long long i = (long long)blockIdx.x * kSelThreads + threadIdx.x; i < n; i += stride) {
+            const float x = __ldg(loss_px + i);
+            if (key_of(x) > kth_key) a += (double)x;
+        }
+    }
+    const double cta_sum = block_sum<kSelThreads>(a, red);
+    if (threadIdx.x == 0) ws->sel_partials[blockIdx.x] = cta_sum;
+    grid.sync();
+    if (blockIdx.x == 0) {
+        double b = 0.0;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += kSelThreads) b += __ldcg(&ws->sel_partials[i]);
+        const double sum_gt = block_sum<kSelThreads>(b, red);
+        if (threadIdx.x == 0) {
+            const unsigned long long take = p3.k_rem;               // ties kept (1 .. p3.cnt)
+            const double sum_kept = sum_gt + (double)take * (double)kth;
+            st.loss = (float)(sum_kept / (double)k); st.kth = kth; st.tie_share = (float)((double)take / (double)p3.cnt);
+            st.inv_denom = (float)(1.0 / (double)k); st.branch = 2; st.n_kept = k; st.sum_kept = sum_kept;
+            ws->state = st;
+            if (loss_out) *loss_out = st.loss;
+        }
+    }
+}
+
+int launch_finalize(const float* loss_px, long long n_px, float thresh, void* ws, float* loss_out, void* stream) {
+    Workspace* w = reinterpret_cast<Workspace*>(ws);
+    int grid = thresh < 0.f ? 1 : std::min(sm_count(), kMaxCtas);
+    void* args[] = {(void*)&loss_px, (void*)&n_px, (void*)&thresh, (void*)&w, (void*)&loss_out};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)finalize_kernel, dim3(grid), dim3(kSelThreads), args, 0,
+                                                reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaGetLastError();
+}
+
+}  // namespace sf

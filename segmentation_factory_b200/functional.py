@@ -1,0 +1,155 @@
+"""Tensor-level entry points over the C ABI: pointers, shapes and the current CUDA stream.
+
+PyTorch is used for device memory, streams and autograd bookkeeping only; all per-pixel work
+happens in libsegfactory.so.  Nothing here synchronises with the host.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _lib
+
+_LOGIT_CODE = {torch.float32: _lib.SF_F32, torch.bfloat16: _lib.SF_BF16, torch.float16: _lib.SF_F16}
+_LABEL_CODE = {torch.int64: _lib.SF_I64, torch.uint8: _lib.SF_U8}
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def prep_logits(logits: torch.Tensor) -> torch.Tensor:
+    if not isinstance(logits, torch.Tensor) or logits.dim() != 4:
+        raise ValueError("logits must be a [B, C, h, w] tensor")
+    if not logits.is_cuda:
+        raise _lib.SegFactoryError("segmentation_factory_b200 has no CPU path: logits must be a CUDA tensor")
+    if logits.dtype not in _LOGIT_CODE:
+        raise TypeError(f"logits dtype {logits.dtype} not supported (float32, bfloat16, float16)")
+    return logits.contiguous()
+
+
+def prep_labels(labels: torch.Tensor, B: int, size=None) -> torch.Tensor:
+    """Labels as [B, H, W] int64/uint8 on the device.  A flattened vector (engine.py:91 passes
+    labels.flatten()) is reshaped with `size`, which defaults to the logits' own spatial size."""
+    if not labels.is_cuda:
+        raise _lib.SegFactoryError("segmentation_factory_b200 has no CPU path: labels must be a CUDA tensor")
+    if labels.dtype not in _LABEL_CODE:
+        labels = labels.long()
+    if labels.dim() != 3:
+        if size is None:
+            raise ValueError("flattened labels need size=(H, W)")
+        H, W = size
+        if labels.numel() != B * H * W:
+            raise ValueError(f"labels have {labels.numel()} elements, expected {B}*{H}*{W}")
+        labels = labels.reshape(B, H, W)
+    if labels.shape[0] != B:
+        raise ValueError(f"batch mismatch: logits {B}, labels {labels.shape[0]}")
+    return labels.contiguous()
+
+
+def _class_w(weight, C, device):
+    if weight is None:
+        return None
+    w = weight.detach().to(device=device, dtype=torch.float32).contiguous()
+    if w.numel() != C:
+        raise ValueError(f"class weight has {w.numel()} entries, expected {C}")
+    return w
+
+
+def eval_hist(logits: torch.Tensor, labels: torch.Tensor, ignore: int, hist: torch.Tensor, size=None) -> None:
+    """hist[C, C] (int64, device) += confusion counts of argmax(upsample(logits)) vs labels."""
+    logits = prep_logits(logits)
+    B, C, h, w = logits.shape
+    labels = prep_labels(labels, B, size if size is not None else (h, w))
+    if hist.dtype != torch.int64 or not hist.is_contiguous() or hist.numel() != C * C or hist.device != logits.device:
+        raise ValueError("hist must be a contiguous int64 [C, C] tensor on the logits' device")
+    _, H, W = labels.shape
+    with torch.cuda.device(logits.device):
+        rc = _lib.lib().sf_eval_hist(_ptr(logits), _LOGIT_CODE[logits.dtype], _ptr(labels), _LABEL_CODE[labels.dtype],
+                                     B, C, h, w, H, W, int(ignore), _ptr(hist), _stream(logits.device))
+    _lib.check(rc, "sf_eval_hist")
+
+
+def hist_pairs(a: torch.Tensor, b: torch.Tensor, C: int, mat: torch.Tensor) -> None:
+    """mat[C, C] (int64) += bincount(C * a[k] + b[k]) with k = (a >= 0) & (a < C)  (util/utils.py:106-109)."""
+    if not (a.is_cuda and b.is_cuda):
+        raise _lib.SegFactoryError("segmentation_factory_b200 has no CPU path: index vectors must be CUDA tensors")
+    a = a.reshape(-1)
+    b = b.reshape(-1)
+    if a.dtype not in _LABEL_CODE:
+        a = a.long()
+    a = a.contiguous()
+    b = b.long().contiguous()
+    if a.numel() != b.numel():
+        raise ValueError("a and b must have the same number of elements")
+    with torch.cuda.device(a.device):
+        rc = _lib.lib().sf_hist_pairs(_ptr(a), _LABEL_CODE[a.dtype], _ptr(b), a.numel(), int(C), _ptr(mat), _stream(a.device))
+    _lib.check(rc, "sf_hist_pairs")
+
+
+class _FusedCE(torch.autograd.Function):
+    """upsample + (OHEM) cross-entropy; forward = sf_ce_forward + sf_loss_finalize, backward = sf_ce_backward."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, class_w, ignore, thresh, hist):
+        L = _lib.lib()
+        B, C, h, w = logits.shape
+        _, H, W = labels.shape
+        dev = logits.device
+        n_px = B * H * W
+        ohem = thresh >= 0.0
+        need_grad = ctx.needs_input_grad[0]
+        ws_bytes = L.sf_workspace_bytes()
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        loss_px = torch.empty(n_px, dtype=torch.float32, device=dev) if ohem else None
+        lse_px = torch.empty(n_px, dtype=torch.float32, device=dev) if need_grad else None
+        out = torch.empty((), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            st = _stream(dev)
+            rc = L.sf_ce_forward(_ptr(logits), _LOGIT_CODE[logits.dtype], _ptr(labels), _LABEL_CODE[labels.dtype],
+                                 B, C, h, w, H, W, int(ignore), _ptr(class_w), float(thresh),
+                                 _ptr(loss_px), _ptr(lse_px), _ptr(hist), _ptr(ws), ws_bytes, st)
+            _lib.check(rc, "sf_ce_forward")
+            rc = L.sf_loss_finalize(_ptr(loss_px), n_px, float(thresh), _ptr(ws), ws_bytes, _ptr(out), st)
+            _lib.check(rc, "sf_loss_finalize")
+        ctx.ignore = int(ignore)
+        ctx.ws = ws                      # plain attribute: the workspace is an opaque device scratch
+        ctx.save_for_backward(logits, labels, class_w, loss_px, lse_px)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        logits, labels, class_w, loss_px, lse_px = ctx.saved_tensors
+        L = _lib.lib()
+        B, C, h, w = logits.shape
+        _, H, W = labels.shape
+        dev = logits.device
+        g = grad_out.detach().to(device=dev, dtype=torch.float32).contiguous()
+        grad = torch.empty_like(logits)
+        with torch.cuda.device(dev):
+            rc = L.sf_ce_backward(_ptr(logits), _LOGIT_CODE[logits.dtype], _ptr(labels), _LABEL_CODE[labels.dtype],
+                                  B, C, h, w, H, W, ctx.ignore, _ptr(class_w), _ptr(loss_px), _ptr(lse_px),
+                                  _ptr(g), _ptr(ctx.ws), _ptr(grad), _stream(dev))
+        _lib.check(rc, "sf_ce_backward")
+        return grad, None, None, None, None, None
+
+
+def fused_cross_entropy(logits, labels, weight=None, ignore_index=255, ohem_thresh=None, hist=None):
+    """Scalar loss of CrossEntropy (ohem_thresh=None) or OhemCrossEntropy (ohem_thresh = -log(0.7))
+    on logits that may be lower-resolution than the labels.  `hist`, if given, is an int64 [C, C]
+    tensor that additionally receives the confusion counts of the same pass."""
+    logits = prep_logits(logits)
+    B, C, h, w = logits.shape
+    labels = prep_labels(labels, B, (h, w))
+    cw = _class_w(weight, C, logits.device)
+    thresh = -1.0 if ohem_thresh is None else float(ohem_thresh)
+    if ohem_thresh is not None and not (thresh >= 0.0 and math.isfinite(thresh)):
+        raise ValueError("ohem_thresh must be a finite non-negative loss value")
+    if hist is not None and (hist.dtype != torch.int64 or hist.numel() != C * C or not hist.is_contiguous()):
+        raise ValueError("hist must be a contiguous int64 [C, C] tensor")
+    return _FusedCE.apply(logits, labels, cw, int(ignore_index), thresh, hist)

@@ -1,0 +1,132 @@
+"""Drop-in mirror of util/metrics.py:Metrics (semantic-segmentation part) and util/utils.py:ConfusionMatrix.
+
+`update` runs the fused upsample+argmax+histogram kernel; everything O(C^2) (compute_*, reduce) stays
+as the reference's own tensor expressions on the accumulated matrix, so the derived numbers are
+bit-identical once the matrix is.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+from .functional import eval_hist, hist_pairs
+
+__all__ = ["Metrics", "ConfusionMatrix", "fused_eval_update"]
+
+
+class Metrics:
+    """util/metrics.py:9-49,108-114.
+
+    `hist` is float32 like the reference's and receives the same per-call `hist += int64_counts`
+    (inexact past 2**24 per cell, reproduced as is).  `hist_i64` is an exact shadow;
+    it is what gets all-reduced (integer SUM is order-independent), after which `hist` is refreshed from it.
+    """
+
+    def __init__(self, num_classes: int, ignore_label: int, device) -> None:
+        self.ignore_label = ignore_label
+        self.num_classes = num_classes
+        self.hist = torch.zeros(num_classes, num_classes).to(device)
+        self.hist_i64 = torch.zeros(num_classes, num_classes, dtype=torch.int64).to(device)
+        self.device = device
+
+    def _accumulate(self, counts: Tensor) -> None:
+        self.hist += counts                   # float32 += int64, exactly the reference's update expression
+        self.hist_i64 += counts
+
+    def update(self, pred: Tensor, target: Tensor, size=None) -> None:
+        """pred: [B, C, h, w] logits at any resolution; target: [B, H, W] labels, or the flattened vector
+        engine.py:91 passes (then H, W = `size`, defaulting to pred's own h, w)."""
+        counts = torch.zeros(self.num_classes, self.num_classes, dtype=torch.int64, device=pred.device)
+        eval_hist(pred, target, self.ignore_label, counts, size)
+        self._accumulate(counts)
+
+    def compute_iou(self):
+        ious = self.hist.diag() / (self.hist.sum(0) + self.hist.sum(1) - self.hist.diag())
+        miou = ious[~ious.isnan()].mean().item()
+        ious *= 100
+        miou *= 100
+        return ious.cpu().numpy().round(2).tolist(), round(miou, 2)
+
+    def compute_f1(self):
+        f1 = 2 * self.hist.diag() / (self.hist.sum(0) + self.hist.sum(1))
+        mf1 = f1[~f1.isnan()].mean().item()
+        f1 *= 100
+        mf1 *= 100
+        return f1.cpu().numpy().round(2).tolist(), round(mf1, 2)
+
+    def compute_pixel_acc(self):
+        acc = self.hist.diag() / self.hist.sum(1)
+        macc = acc[~acc.isnan()].mean().item()
+        acc *= 100
+        macc *= 100
+        return acc.cpu().numpy().round(2).tolist(), round(macc, 2)
+
+    def reduce_from_all_processes(self):
+        if not dist.is_available() or not dist.is_initialized():
+            return
+        dist.all_reduce(self.hist_i64)        # one int64 [C, C] SUM over NVLink; no barrier needed
+        self.hist = self.hist_i64.to(torch.float32)
+
+
+class ConfusionMatrix(object):
+    """util/utils.py:94-143 (int64 matrix; the source of the reported mIoU and of best-checkpoint selection)."""
+
+    def __init__(self, num_classes):
+        self.num_classes = num_classes
+        self.mat = None
+
+    def _ensure(self, device):
+        if self.mat is None:
+            n = self.num_classes
+            self.mat = torch.zeros((n, n), dtype=torch.int64, device=device)
+
+    def update(self, a, b):
+        """a: flattened labels, b: flattened predicted class indices (engine.py:90)."""
+        self._ensure(a.device)
+        with torch.no_grad():
+            hist_pairs(a, b, self.num_classes, self.mat)
+
+    def update_from_logits(self, labels: Tensor, logits: Tensor, ignore_label: int = 255, size=None):
+        """Fused form: argmax of the (upsampled) logits is taken in-kernel, nothing is materialised."""
+        self._ensure(logits.device)
+        with torch.no_grad():
+            eval_hist(logits, labels, ignore_label, self.mat, size)
+
+    def reset(self):
+        if self.mat is not None:
+            self.mat.zero_()
+
+    def compute(self):
+        h = self.mat.float()
+        acc_global = torch.diag(h).sum() / h.sum()
+        acc = torch.diag(h) / h.sum(1)
+        iu = torch.diag(h) / (h.sum(1) + h.sum(0) - torch.diag(h))
+        return acc_global, acc, iu
+
+    def reduce_from_all_processes(self):
+        if not dist.is_available() or not dist.is_initialized():
+            return
+        dist.all_reduce(self.mat)
+
+    def __str__(self):
+        acc_global, acc, iu = self.compute()
+        return (
+            'global correct: {:.1f}\n'
+            'average row correct: {}\n'
+            'IoU: {}\n'
+            'mean IoU: {:.1f}').format(
+                acc_global.item() * 100,
+                ['{:.1f}'.format(i) for i in (acc * 100).tolist()],
+                ['{:.1f}'.format(i) for i in (iu * 100).tolist()],
+                iu.mean().item() * 100)
+
+
+def fused_eval_update(logits: Tensor, labels: Tensor, metric: Metrics, confmat: ConfusionMatrix, size=None) -> None:
+    """One kernel launch feeding both accumulators of engine.evaluate (engine.py:90-91): the reference takes
+    two argmax passes over materialised full-resolution logits and builds two histograms."""
+    counts = torch.zeros(metric.num_classes, metric.num_classes, dtype=torch.int64, device=logits.device)
+    eval_hist(logits, labels, metric.ignore_label, counts, size)
+    metric._accumulate(counts)
+    confmat._ensure(logits.device)
+    confmat.mat += counts
