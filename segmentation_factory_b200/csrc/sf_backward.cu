@@ -41,12 +41,14 @@ struct BwdParams {
     int B, C, ignore, label_u8;
     int tbw, tiles_x, tiles_y, n_chunks;
     int box_w, dmax, use_tma, src_bytes;
+    int xalign;                              // TMA inner coordinate granularity (16 bytes) in elements
 };
 
 __host__ __device__ __forceinline__ int first_dst_clamped(const Axis& ax, int i) {   // first d with src_i0(d) >= i
     return i <= 0 ? 0 : first_dst_of(ax, i);
 }
 __device__ __forceinline__ int swz(int x) { return x + (x >> 5); }
+__host__ __device__ __forceinline__ int floor_al_b(int x, int a) { return x & ~(a - 1); }   // also right for x = -1
 
 template <int NCH>
 __device__ __forceinline__ void onehot_sub(int yk, float (&a0)[NCH], float (&a1)[NCH], float v0, float v1) {
@@ -85,21 +87,22 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmap, const BwdParams p) {
     const int nvalid = min(NCH, p.C - c0);
     const int Xa = first_dst_clamped(p.ax, ja - 1), Xb = first_dst_clamped(p.ax, jb);
     const int Ya = first_dst_clamped(p.ay, ia - 1), Yb = first_dst_clamped(p.ay, ib);
+    const int jO = floor_al_b(ja - 1, p.xalign);                    // box x-origin (16-byte aligned, may be negative)
 
-    // ---- stage the low-res tile (rows ia-1 .. ia+TH, cols ja-1 .. ja-1+box_w) ----
+    // ---- stage the low-res tile (rows ia-1 .. ia+TH, cols jO .. jO+box_w) ----
     if (p.use_tma) {
         if (tid == 0) {
             mbar_init(bar, 1);
             mbar_fence_init();
             mbar_expect_tx(bar, (uint32_t)(NCH * kBwdBH * p.box_w * (int)sizeof(LT)));
-            tma_load_3d(S, &tmap, bar, ja - 1, ia - 1, b * p.C + c0);
+            tma_load_3d(S, &tmap, bar, jO, ia - 1, b * p.C + c0);
         }
     } else {
         const LT* src = reinterpret_cast<const LT*>(p.logits);
         const int n = NCH * kBwdBH * p.box_w;
         for (int e = tid; e < n; e += kBwdThreads) {
             const int col = e % p.box_w, row = (e / p.box_w) % kBwdBH, k = e / (p.box_w * kBwdBH);
-            const int ch = c0 + k, i = ia - 1 + row, j = ja - 1 + col;
+            const int ch = c0 + k, i = ia - 1 + row, j = jO + col;
             LT v = LT(0.0f);
             if (ch < p.C && i >= 0 && i < h && j >= 0 && j < w) v = src[(((long long)b * p.C + ch) * h + i) * w + j];
             S[e] = v;
@@ -127,7 +130,7 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmap, const BwdParams p) {
     const int X = Xa + tid;
     const bool colok = X < Xb;
     const Tap tc = make_tap<LT>(p.ax, colok ? X : max(Xb - 1, 0));
-    const int j0l = tc.i0 - (ja - 1), j1l = tc.i1 - (ja - 1);
+    const int j0l = tc.i0 - jO, j1l = tc.i1 - jO;
     const float lw0 = tc.l0, lw1 = tc.l1;
 
     const sf_loss_state* stp = &p.ws->state;
@@ -297,14 +300,18 @@ int launch_backward(const BwdArgs& a) {
     if (grid >= (1LL << 31)) return SF_ERR_SHAPE;
 
     const int align = 16 / esz;
-    p.box_w = (tbw + 2 + align - 1) / align * align;
+    p.xalign = align;
+    int span = 1;
+    for (int ja = 0; ja < a.w; ja += tbw) span = std::max(span, std::min(ja + tbw, a.w - 1) - floor_al_b(ja - 1, align) + 1);
+    p.box_w = (span + align - 1) / align * align;
+    if (p.box_w > 256) return SF_ERR_SHAPE;
     p.src_bytes = ((nch * kBwdBH * p.box_w * esz) + 127) & ~127;
     const size_t smem = (size_t)p.src_bytes + (size_t)2 * nch * kBwdRP * 4 + (size_t)dmax * kBwdTBWP * 4 + kBwdTBWP * 4 + 16;
     if (smem > 227 * 1024) return SF_ERR_SHAPE;
 
     CUtensorMap tmap{};
     p.use_tma = 0;
-    if (!a.force_no_tma && ((size_t)a.w * esz) % 16 == 0 && ((uintptr_t)a.logits % 16) == 0) {
+    if (!a.force_no_tma && ((size_t)a.w * esz) % 16 == 0 && ((uintptr_t)a.logits % 16) == 0 && p.box_w <= a.w && kBwdBH <= a.h) {
         const int rc = make_logits_tmap(&tmap, a.logits, a.ldtype, a.B * a.C, a.h, a.w, nch, kBwdBH, p.box_w);
         if (rc != 0) return rc;
         p.use_tma = 1;

@@ -43,11 +43,14 @@ struct FwdParams {
     int tiles_x, tiles_y, total_tiles;
     int n_chunks, n_passes, box_w;
     int use_tma;
+    int xalign;                            // box x-origin granularity in elements: TMA needs 16-byte aligned inner coordinates
     int stage_bytes;                       // bytes of one smem stage (128-aligned)
     int hist_bytes;                        // bytes reserved for the smem histogram (16-aligned)
 };
 
 struct ItemCoord { int b, ua, Xa, pass, chunk; };
+
+__host__ __device__ __forceinline__ int floor_al(int x, int a) { return x & ~(a - 1); }   // a is a power of two
 
 template <int NCH>
 __device__ __forceinline__ ItemCoord decode_item(const FwdParams& p, int n) {
@@ -68,7 +71,7 @@ __device__ __forceinline__ ItemCoord decode_item(const FwdParams& p, int n) {
 template <typename LT, int NCH>
 __device__ __forceinline__ void issue_tma(const FwdParams& p, const CUtensorMap* tmap, const ItemCoord& c,
                                           unsigned char* stage, uint64_t* bar) {
-    const int jA = src_i0(p.ax, c.Xa);
+    const int jA = floor_al(src_i0(p.ax, c.Xa), p.xalign);
     mbar_expect_tx(bar, (uint32_t)(NCH * kFwdBH * p.box_w * (int)sizeof(LT)));
     tma_load_3d(stage, tmap, bar, jA, c.ua, c.b * p.C + c.chunk * NCH);
 }
@@ -76,14 +79,14 @@ __device__ __forceinline__ void issue_tma(const FwdParams& p, const CUtensorMap*
 // Fallback loader for shapes TMA cannot describe (row pitch not a multiple of 16 bytes).
 template <typename LT, int NCH>
 __device__ __forceinline__ void load_plain(const FwdParams& p, const ItemCoord& c, LT* stage) {
-    const int jA = src_i0(p.ax, c.Xa);
+    const int jA = floor_al(src_i0(p.ax, c.Xa), p.xalign);
     const LT* src = reinterpret_cast<const LT*>(p.logits);
     const int n = NCH * kFwdBH * p.box_w;
     for (int e = threadIdx.x; e < n; e += kFwdThreads) {
         const int col = e % p.box_w, row = (e / p.box_w) % kFwdBH, k = e / (p.box_w * kFwdBH);
         const int ch = c.chunk * NCH + k, i = c.ua + row, j = jA + col;
         LT v = LT(0.0f);
-        if (ch < p.C && i >= 0 && i < p.ay.in && j < p.ax.in)
+        if (ch < p.C && i >= 0 && i < p.ay.in && j >= 0 && j < p.ax.in)
             v = src[(((long long)c.b * p.C + ch) * p.ay.in + i) * p.ax.in + j];
         stage[e] = v;
     }
@@ -146,7 +149,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap, const FwdParams p) {
             X = c.Xa + tx;
             colok = X < p.ax.out;
             const Tap tc = make_tap<LT>(p.ax, colok ? X : p.ax.out - 1);
-            const int jA = src_i0(p.ax, c.Xa);
+            const int jA = floor_al(src_i0(p.ax, c.Xa), p.xalign);
             j0r = tc.i0 - jA; j1r = tc.i1 - jA; lw0 = tc.l0; lw1 = tc.l1;
             const int u = c.ua + gy;                               // my group's (unclamped) source row
             int y0 = p.ay.out, y1 = p.ay.out;
@@ -358,13 +361,14 @@ int launch_forward(const FwdArgs& a) {
     for (int u = p.ay.ident ? 0 : -1; u < a.h; ++u)
         max_rows = std::max(max_rows, first_dst_of(p.ay, u + 1) - first_dst_of(p.ay, u));
     p.n_passes = (max_rows + kFwdG - 1) / kFwdG;
+    const int align = 16 / esz;
+    p.xalign = align;
     int span = 1;
     for (int t = 0; t < p.tiles_x; ++t) {
         const int xa = t * kFwdTW, xb = std::min(xa + kFwdTW, a.W) - 1;
         const int jb = src_i0(p.ax, xb);
-        span = std::max(span, jb + (jb < a.w - 1 && !p.ax.ident ? 1 : 0) - src_i0(p.ax, xa) + 1);
+        span = std::max(span, jb + (jb < a.w - 1 && !p.ax.ident ? 1 : 0) - floor_al(src_i0(p.ax, xa), align) + 1);
     }
-    const int align = 16 / esz;
     p.box_w = (span + align - 1) / align * align;
     if (p.box_w > 256) return SF_ERR_SHAPE;
     p.stage_bytes = ((nch * kFwdBH * p.box_w * esz) + 127) & ~127;
@@ -376,7 +380,9 @@ int launch_forward(const FwdArgs& a) {
 
     CUtensorMap tmap{};
     p.use_tma = 0;
-    if (!a.force_no_tma && ((size_t)a.w * esz) % 16 == 0 && ((uintptr_t)a.logits % 16) == 0) {
+    // TMA needs 16-byte aligned rows and (observed on B200, driver 580) a box no wider than the tensor row;
+    // tiny or odd-pitch maps take the plain cooperative loader instead
+    if (!a.force_no_tma && ((size_t)a.w * esz) % 16 == 0 && ((uintptr_t)a.logits % 16) == 0 && p.box_w <= a.w && kFwdBH <= a.h) {
         const int rc = make_logits_tmap(&tmap, a.logits, a.ldtype, a.B * a.C, a.h, a.w, nch, kFwdBH, p.box_w);
         if (rc != 0) return rc;
         p.use_tma = 1;
