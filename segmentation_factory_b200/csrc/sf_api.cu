@@ -18,6 +18,10 @@ bool env_no_tma() {
     const char* e = std::getenv("SF_NO_TMA");
     return e && e[0] == '1';
 }
+bool env_no_fast() {
+    const char* e = std::getenv("SF_NO_FAST");
+    return e && e[0] == '1';
+}
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

@@ -1,0 +1,341 @@
+// sf_forward_fast.cu -- integer-scale, all-channels-in-registers specialisation of the fused forward.
+//
+// Same contract and same arithmetic as sf_forward.cu (bit-identical argmax / matrix, same loss formula); used
+// when H == S*h, W == S*w, S in {2,4,8} and C is one of the instantiated class counts.  What changes is the
+// schedule (measured on B200, profiles/r01_v1_*: the generic kernel issued 34 instructions per pixel-channel,
+// two thirds of them integer/addressing/setup):
+//   * a thread owns one label column and walks a strip of GPS row groups (GPS*S rows): the horizontal lerps of a
+//     source row are computed once and the bottom row of one group is reused as the top row of the next;
+//   * geometry is constexpr (sf_fast.cuh), shared-memory offsets fold into LDS immediates;
+//   * vertical lerp, exp argument and exp sum run as packed fp32x2 over channel pairs (FFMA2/FMUL2/FADD2);
+//   * labels of the next group are prefetched while the current one is computed;
+//   * a NaN in the logits is detected for free (the exp sum turns NaN) and resolved on a rare slow path.
+// Tile = 64 columns x 4 strips x GPS groups; one TMA box [C][4*GPS+1][BW] per tile, 2-stage mbarrier pipeline,
+// persistent CTAs (2 per SM).
+#include "sf_fast.cuh"
+#include "sf_launch.h"
+
+namespace sf {
+
+constexpr int kFfTW = 64, kFfStrips = 4, kFfThreads = kFfTW * kFfStrips, kFfStages = 2;
+
+struct FfParams {
+    const void* labels;
+    const float* class_w;
+    float* loss_px;
+    float* lse_px;
+    unsigned long long* hist;
+    Workspace* ws;
+    int B, h, w, H, W, ignore, label_u8;
+    float thresh;
+    int tiles_x, tiles_y, total_tiles;
+};
+
+template <typename LT, int C, int S>
+struct FfGeom {
+    static constexpr int GPS = 16 / S >= 2 ? 16 / S : 2;            // 16 rows per strip (S=8: 2 groups)
+    static constexpr int NGT = kFfStrips * GPS;                     // groups per tile
+    static constexpr int BH = NGT + 1;
+    static constexpr int XAL = 16 / (int)sizeof(LT);
+    static constexpr int BW = round_up(XAL + kFfTW / S + 1, XAL);
+    static constexpr int PLANE = BH * BW;
+    static constexpr int STAGE_BYTES = round_up(C * PLANE * (int)sizeof(LT), 128);
+    static constexpr int NP = C / 2;                                // channel pairs; channel C-1 is the odd tail
+    static constexpr bool ODD = (C & 1) != 0;
+};
+
+template <typename LT, int C, int S, bool SOFTMAX>
+__global__ void __launch_bounds__(kFfThreads, 2)
+fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
+    using G = FfGeom<LT, C, S>;
+    using TP = ScaleTap<S>;
+    constexpr int NP = G::NP;
+    extern __shared__ __align__(128) unsigned char smem[];
+    int* hist_s = reinterpret_cast<int*>(smem + kFfStages * G::STAGE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kFfStages * G::STAGE_BYTES + round_up(C * C * 4, 16));
+    __shared__ double red_scratch[kFfThreads / 32];
+
+    const int tid = threadIdx.x;
+    const int tx = tid % kFfTW, sy = tid / kFfTW;
+    const bool want_hist = p.hist != nullptr;
+
+    if (want_hist)
+        for (int k = tid; k < C * C; k += kFfThreads) hist_s[k] = 0;
+    if (tid == 0) {
+        tma_prefetch_desc(&tmap);
+        for (int s = 0; s < kFfStages; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int per_img = p.tiles_x * p.tiles_y;
+    int n_tiles = 0;
+    if ((int)blockIdx.x < p.total_tiles) n_tiles = (p.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1;
+
+    auto issue = [&](int n) {
+        const int tile = blockIdx.x + n * gridDim.x;
+        const int b = tile / per_img, r = tile % per_img;
+        const int ua = -1 + (r / p.tiles_x) * G::NGT;
+        const int jO = (r % p.tiles_x) * (kFfTW / S) - G::XAL;
+        uint64_t* bar = &full[n % kFfStages];
+        mbar_expect_tx(bar, (uint32_t)(C * G::PLANE * (int)sizeof(LT)));
+        tma_load_3d(smem + (n % kFfStages) * G::STAGE_BYTES, &tmap, bar, jO, ua, b * C);
+    };
+    if (tid == 0)
+        for (int n = 0; n < kFfStages && n < n_tiles; ++n) issue(n);
+
+    double acc_loss = 0.0, acc_w = 0.0, acc_hard = 0.0;
+    unsigned int cnt_valid = 0, cnt_hard = 0;
+    const float2 l2e2 = splat(kLog2e);
+
+    for (int n = 0; n < n_tiles; ++n) {
+        const int tile = blockIdx.x + n * gridDim.x;
+        const int b = tile / per_img, rr = tile % per_img;
+        const int ua = -1 + (rr / p.tiles_x) * G::NGT;
+        const int Xa = (rr % p.tiles_x) * kFfTW;
+        const int X = Xa + tx;
+        const bool colok = X < p.W;
+        int j0, j1; float lw0, lw1;
+        TP::get(colok ? X : p.W - 1, p.w, j0, j1, lw0, lw1);
+        const int jO = Xa / S - G::XAL;
+        const LT* Sg = reinterpret_cast<const LT*>(smem + (n % kFfStages) * G::STAGE_BYTES);
+        const LT* c0p = Sg + (j0 - jO);                            // column taps inside the box
+        const LT* c1p = Sg + (j1 - jO);
+        const float2 lw0_2 = splat(lw0), lw1_2 = splat(lw1);
+
+        const int u_first = ua + sy * G::GPS;
+        // labels of the first group (later groups are prefetched one group ahead)
+        int lab_nxt[S];
+        auto fetch_labels = [&](int u) {
+            #pragma unroll
+            for (int r = 0; r < S; ++r) lab_nxt[r] = -1;
+            if (u <= p.h - 1 && colok) {
+                const int y0 = TP::first(u), cnt = TP::count(u, p.h);
+                const long long base = ((long long)b * p.H + y0) * p.W + X;
+                #pragma unroll
+                for (int r = 0; r < S; ++r)
+                    if (r < cnt) {
+                        const long long y = ld_label(p.labels, p.label_u8, base + (long long)r * p.W);
+                        lab_nxt[r] = (y != p.ignore && y >= 0 && y < C) ? (int)y : -1;
+                    }
+            }
+        };
+        fetch_labels(u_first);
+
+        mbar_wait(&full[n % kFfStages], (uint32_t)((n / kFfStages) & 1));
+
+        float2 tt[NP > 0 ? NP : 1], tb[NP > 0 ? NP : 1];
+        float ttl = 0.f, tbl = 0.f;                                  // odd tail channel C-1
+        auto hrow = [&](int row, float2 (&t)[NP > 0 ? NP : 1], float& tl) {   // horizontal lerps of one box row
+            const LT* q0 = c0p + row * G::BW;
+            const LT* q1 = c1p + row * G::BW;
+            #pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                const float2 a = make_float2(Logit<LT>::ld(q0 + (2 * q) * G::PLANE), Logit<LT>::ld(q0 + (2 * q + 1) * G::PLANE));
+                const float2 c = make_float2(Logit<LT>::ld(q1 + (2 * q) * G::PLANE), Logit<LT>::ld(q1 + (2 * q + 1) * G::PLANE));
+                t[q] = lerp2_pinned(a, lw0_2, c, lw1_2);
+            }
+            if (G::ODD) tl = lerp_pinned(Logit<LT>::ld(q0 + (C - 1) * G::PLANE), lw0, Logit<LT>::ld(q1 + (C - 1) * G::PLANE), lw1);
+        };
+
+        float tile_loss = 0.f, tile_w = 0.f, tile_hard = 0.f;
+        int u_prev = -2;
+        #pragma unroll 1
+        for (int g = 0; g < G::GPS; ++g) {
+            const int u = u_first + g;
+            if (u > p.h - 1) break;                                  // uniform per warp (a warp shares sy)
+            int lab[S];
+            #pragma unroll
+            for (int r = 0; r < S; ++r) lab[r] = lab_nxt[r];
+            if (g + 1 < G::GPS) fetch_labels(u + 1);
+
+            const int i0 = max(u, 0), i1 = min(i0 + 1, p.h - 1);
+            if (u_prev == -2) {
+                hrow(i0 - ua, tt, ttl);
+                hrow(i1 - ua, tb, tbl);
+            } else if (u_prev >= 0) {                                // u_prev == -1: same (row 0, row 1) pair again
+                #pragma unroll
+                for (int q = 0; q < NP; ++q) tt[q] = tb[q];
+                ttl = tbl;
+                hrow(i1 - ua, tb, tbl);
+            }
+            u_prev = u;
+            float nanflag = 0.f;
+            if (!SOFTMAX) {
+                #pragma unroll
+                for (int q = 0; q < NP; ++q) nanflag = __fmaf_rn(tb[q].x + tb[q].y, 0.f, __fmaf_rn(tt[q].x + tt[q].y, 0.f, nanflag));
+                if (G::ODD) nanflag = __fmaf_rn(tbl, 0.f, __fmaf_rn(ttl, 0.f, nanflag));
+            }
+
+            const int cnt = TP::count(u, p.h);
+            const int y0 = TP::first(u);
+            #pragma unroll
+            for (int r = 0; r < S; ++r) {
+                if (r < cnt) {                                       // uniform
+                    const float lh1 = u < 0 ? 0.0f : ((float)r + 0.5f) * (1.0f / S);
+                    const float lh0 = 1.0f - lh1;
+                    const float2 lh0_2 = splat(lh0), lh1_2 = splat(lh1);
+                    float2 z[NP > 0 ? NP : 1];
+                    float zl = 0.f;
+                    #pragma unroll
+                    for (int q = 0; q < NP; ++q) z[q] = rnd2<LT>(lerp2_pinned(tt[q], lh0_2, tb[q], lh1_2));
+                    if (G::ODD) zl = Logit<LT>::rnd(lerp_pinned(ttl, lh0, tbl, lh1));
+                    // first-max argmax
+                    float m; int idx = 0;
+                    if (NP > 0) {
+                        m = z[0].x;
+                        if (z[0].y > m) { m = z[0].y; idx = 1; }
+                        #pragma unroll
+                        for (int q = 1; q < NP; ++q) {
+                            if (z[q].x > m) { m = z[q].x; idx = 2 * q; }
+                            if (z[q].y > m) { m = z[q].y; idx = 2 * q + 1; }
+                        }
+                        if (G::ODD && zl > m) { m = zl; idx = C - 1; }
+                    } else {
+                        m = zl;
+                    }
+                    float ssum = 1.f;
+                    const float m2 = __fmul_rn(m, kLog2e);
+                    if (SOFTMAX) {
+                        const float2 nm2 = splat(-m2);
+                        float2 a2 = make_float2(0.f, 0.f);
+                        #pragma unroll
+                        for (int q = 0; q < NP; ++q) {
+                            const float2 e = __ffma2_rn(z[q], l2e2, nm2);
+                            a2 = __fadd2_rn(a2, make_float2(ex2_approx(e.x), ex2_approx(e.y)));
+                        }
+                        ssum = a2.x + a2.y;
+                        if (G::ODD) ssum += ex2_approx(__fmaf_rn(zl, kLog2e, -m2));
+                    }
+                    const bool weird = SOFTMAX ? (ssum != ssum) : (nanflag != nanflag);
+                    if (weird) {                                     // torch: NaN beats everything, first NaN wins
+                        #pragma unroll 1
+                        for (int k = C - 1; k >= 0; --k) {
+                            const LT* qa = Sg + k * G::PLANE + (i0 - ua) * G::BW;
+                            const LT* qb = Sg + k * G::PLANE + (i1 - ua) * G::BW;
+                            const float t0 = lerp_pinned(Logit<LT>::ld(qa + (j0 - jO)), lw0, Logit<LT>::ld(qa + (j1 - jO)), lw1);
+                            const float t1 = lerp_pinned(Logit<LT>::ld(qb + (j0 - jO)), lw0, Logit<LT>::ld(qb + (j1 - jO)), lw1);
+                            const float zk = Logit<LT>::rnd(lerp_pinned(t0, lh0, t1, lh1));
+                            if (zk != zk) idx = k;
+                        }
+                    }
+                    const int Y = y0 + r;
+                    const long long px = ((long long)b * p.H + Y) * p.W + X;
+                    if (SOFTMAX && colok) {
+                        const float corr = __fmaf_rn(m, kLog2e, -m2);      // exact residual of rn(m*log2e)
+                        const float lg = (__log2f(ssum) - corr) * kLn2;
+                        float l = 0.f;
+                        if (lab[r] >= 0) {
+                            // label logit: same ops, same bits as the z[] entry of that channel
+                            const LT* qa = Sg + lab[r] * G::PLANE + (i0 - ua) * G::BW;
+                            const LT* qb = Sg + lab[r] * G::PLANE + (i1 - ua) * G::BW;
+                            const float t0 = lerp_pinned(Logit<LT>::ld(qa + (j0 - jO)), lw0, Logit<LT>::ld(qa + (j1 - jO)), lw1);
+                            const float t1 = lerp_pinned(Logit<LT>::ld(qb + (j0 - jO)), lw0, Logit<LT>::ld(qb + (j1 - jO)), lw1);
+                            const float zy = Logit<LT>::rnd(lerp_pinned(t0, lh0, t1, lh1));
+                            const float wy = p.class_w ? __ldg(p.class_w + lab[r]) : 1.f;
+                            l = wy * (lg - (zy - m));
+                            tile_loss += l; tile_w += wy; ++cnt_valid;
+                            if (l > p.thresh) { tile_hard += l; ++cnt_hard; }
+                        }
+                        if (p.loss_px) p.loss_px[px] = l;
+                        if (p.lse_px) p.lse_px[px] = m + lg;
+                    }
+                    if (want_hist) {
+                        const int key = (colok && lab[r] >= 0) ? lab[r] * C + idx : -1;
+                        const unsigned peers = __match_any_sync(0xffffffffu, key);
+                        if (key >= 0 && (int)(tid & 31) == __ffs(peers) - 1) atomicAdd(&hist_s[key], __popc(peers));
+                    }
+                }
+            }
+        }
+        acc_loss += (double)tile_loss; acc_w += (double)tile_w; acc_hard += (double)tile_hard;
+
+        __syncthreads();                                             // all threads are done with this stage
+        if (tid == 0 && n + kFfStages < n_tiles) issue(n + kFfStages);
+    }
+
+    if (want_hist) {
+        for (int k = tid; k < C * C; k += kFfThreads) {
+            const int v = hist_s[k];
+            if (v) atomicAdd(p.hist + k, (unsigned long long)v);
+        }
+    }
+    if (SOFTMAX) {
+        const double r0d = block_sum<kFfThreads>(acc_loss, red_scratch);
+        const double r1d = block_sum<kFfThreads>(acc_w, red_scratch);
+        const double r2d = block_sum<kFfThreads>(acc_hard, red_scratch);
+        const double r3d = block_sum<kFfThreads>((double)cnt_valid, red_scratch);
+        const double r4d = block_sum<kFfThreads>((double)cnt_hard, red_scratch);
+        if (tid == 0) {
+            double* o = p.ws->partials[blockIdx.x];
+            o[0] = r0d; o[1] = r1d; o[2] = r2d; o[3] = r3d; o[4] = r4d;
+            if (blockIdx.x == 0) p.ws->n_partials = gridDim.x;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+template <typename LT, int C, int S, bool SOFTMAX>
+static int ff_launch(const FwdArgs& a) {
+    using G = FfGeom<LT, C, S>;
+    FfParams p{};
+    p.labels = a.labels; p.class_w = a.class_w; p.loss_px = a.loss_px; p.lse_px = a.lse_px; p.hist = a.hist;
+    p.ws = reinterpret_cast<Workspace*>(a.ws);
+    p.B = a.B; p.h = a.h; p.w = a.w; p.H = a.H; p.W = a.W; p.ignore = a.ignore; p.label_u8 = a.ydtype == SF_U8;
+    p.thresh = a.thresh;
+    p.tiles_x = (a.W + kFfTW - 1) / kFfTW;
+    p.tiles_y = (a.h + 1 + G::NGT - 1) / G::NGT;
+    const long long total = (long long)a.B * p.tiles_x * p.tiles_y;
+    if (total >= (1LL << 31)) return SF_ERR_SHAPE;
+    p.total_tiles = (int)total;
+    CUtensorMap tmap{};
+    const int rc = make_logits_tmap(&tmap, a.logits, a.ldtype, a.B * C, a.h, a.w, C, G::BH, G::BW);
+    if (rc != 0) return rc;
+    const size_t smem = (size_t)kFfStages * G::STAGE_BYTES + round_up(C * C * 4, 16) + kFfStages * 8 + 16;
+    auto k = fwd_fast_kernel<LT, C, S, SOFTMAX>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int grid = (int)std::min<long long>(total, std::min(kMaxCtas, 2 * sm_count()));
+    k<<<grid, kFfThreads, smem, reinterpret_cast<cudaStream_t>(a.stream)>>>(tmap, p);
+    return (int)cudaGetLastError();
+}
+
+template <typename LT, int C, int S>
+static int ff_mode(const FwdArgs& a) {
+    return a.softmax ? ff_launch<LT, C, S, true>(a) : ff_launch<LT, C, S, false>(a);
+}
+template <typename LT, int C>
+static int ff_scale(const FwdArgs& a, int s) {
+    switch (s) {
+        case 4: return ff_mode<LT, C, 4>(a);
+        case 8: return ff_mode<LT, C, 8>(a);
+        default: return -1000;
+    }
+}
+template <typename LT>
+static int ff_classes(const FwdArgs& a, int s) {
+    switch (a.C) {
+        case 19: return ff_scale<LT, 19>(a, s);
+        case 21: return ff_scale<LT, 21>(a, s);
+        default: return -1000;
+    }
+}
+
+// Returns -1000 when the shape is not covered (the caller then takes the generic kernel).
+int launch_forward_fast(const FwdArgs& a) {
+    if (a.force_no_tma || a.h <= 0 || a.w <= 0 || a.H % a.h || a.W % a.w) return -1000;
+    const int s = a.H / a.h;
+    if (s != a.W / a.w) return -1000;
+    const int esz = a.ldtype == SF_F32 ? 4 : 2;
+    if (((size_t)a.w * esz) % 16 || ((uintptr_t)a.logits % 16)) return -1000;
+    // the box must not be wider/taller than the tensor (see sf_forward.cu)
+    const int xal = 16 / esz;
+    if (a.w < round_up(xal + kFfTW / s + 1, xal) || a.h < 17) return -1000;
+    if (a.ldtype == SF_F32) return ff_classes<float>(a, s);
+    if (a.ldtype == SF_BF16) return ff_classes<__nv_bfloat16>(a, s);
+    return ff_classes<__half>(a, s);
+}
+
+}  // namespace sf

@@ -22,6 +22,7 @@ struct FwdArgs {
     bool force_no_tma;     // SF_NO_TMA=1 in the environment (debug / A-B measurement)
 };
 int launch_forward(const FwdArgs& a);
+int launch_forward_fast(const FwdArgs& a);    // -1000: shape not covered by the integer-scale specialisation
 
 struct BwdArgs {
     const void* logits; int ldtype;
@@ -46,5 +47,6 @@ int make_logits_tmap(CUtensorMap* map, const void* logits, int ldtype, int plane
                      int box_c, int box_h, int box_w);
 int sm_count();
 bool env_no_tma();
+bool env_no_fast();   // SF_NO_FAST=1: always take the generic kernels (A/B measurement, tests)
 
 }  // namespace sf

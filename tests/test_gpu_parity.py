@@ -135,8 +135,10 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("no_fast", ["0", "1"])
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
-def test_seeded_vs_oracle(sf, oracle, case):
+def test_seeded_vs_oracle(sf, oracle, case, no_fast, monkeypatch):
+    monkeypatch.setenv("SF_NO_FAST", no_fast)                      # 1: force the generic kernels on fast-path shapes
     name, seed, B, C, h, w, H, W, kind, dtype, ldt, lk, weighted = case
     low, lab = _synth(seed, B, C, h, w, H, W, kind, dtype, ldt)
     cw = (torch.rand(C, generator=torch.Generator().manual_seed(7)) + 0.5) if weighted else None
