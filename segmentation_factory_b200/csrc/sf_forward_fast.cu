@@ -104,28 +104,36 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
         const float2 lw0_2 = splat(lw0), lw1_2 = splat(lw1);
 
         const int u_first = ua + sy * G::GPS;
-        // labels of the first group (later groups are prefetched one group ahead)
-        int lab_nxt[S];
+        // Labels travel as one byte each (valid classes < C <= 24 here, 255 = not counted), packed 8 per register
+        // pair.  Raw 64-bit loads for the NEXT group are issued a whole group ahead and only decoded when needed.
+        long long raw[S];
         auto fetch_labels = [&](int u) {
             #pragma unroll
-            for (int r = 0; r < S; ++r) lab_nxt[r] = -1;
+            for (int r = 0; r < S; ++r) raw[r] = -1;
             if (u <= p.h - 1 && colok) {
                 const int y0 = TP::first(u), cnt = TP::count(u, p.h);
                 const long long base = ((long long)b * p.H + y0) * p.W + X;
                 #pragma unroll
                 for (int r = 0; r < S; ++r)
-                    if (r < cnt) {
-                        const long long y = ld_label(p.labels, p.label_u8, base + (long long)r * p.W);
-                        lab_nxt[r] = (y != p.ignore && y >= 0 && y < C) ? (int)y : -1;
-                    }
+                    if (r < cnt) raw[r] = ld_label(p.labels, p.label_u8, base + (long long)r * p.W);
             }
+        };
+        auto pack_labels = [&]() -> unsigned long long {
+            unsigned long long pk = 0;
+            #pragma unroll
+            for (int r = 0; r < S; ++r) {
+                const long long y = raw[r];
+                const unsigned v = (y != p.ignore && y >= 0 && y < C) ? (unsigned)y : 255u;
+                pk |= (unsigned long long)v << (8 * r);
+            }
+            return pk;
         };
         fetch_labels(u_first);
 
         mbar_wait(&full[n % kFfStages], (uint32_t)((n / kFfStages) & 1));
 
-        float2 tt[NP > 0 ? NP : 1], tb[NP > 0 ? NP : 1];
-        float ttl = 0.f, tbl = 0.f;                                  // odd tail channel C-1
+        float2 ta[NP > 0 ? NP : 1], tb[NP > 0 ? NP : 1];
+        float tal = 0.f, tbl = 0.f;                                  // odd tail channel C-1
         auto hrow = [&](int row, float2 (&t)[NP > 0 ? NP : 1], float& tl) {   // horizontal lerps of one box row
             const LT* q0 = c0p + row * G::BW;
             const LT* q1 = c1p + row * G::BW;
@@ -139,113 +147,130 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
         };
 
         float tile_loss = 0.f, tile_w = 0.f, tile_hard = 0.f;
-        int u_prev = -2;
-        #pragma unroll 1
-        for (int g = 0; g < G::GPS; ++g) {
-            const int u = u_first + g;
-            if (u > p.h - 1) break;                                  // uniform per warp (a warp shares sy)
-            int lab[S];
-            #pragma unroll
-            for (int r = 0; r < S; ++r) lab[r] = lab_nxt[r];
-            if (g + 1 < G::GPS) fetch_labels(u + 1);
 
+        // one row group: `top`/`bot` hold the horizontal lerps of source rows i0 / i1
+        auto do_group = [&](int u, const float2 (&top)[NP > 0 ? NP : 1], float topl,
+                            const float2 (&bot)[NP > 0 ? NP : 1], float botl, unsigned long long labs) {
             const int i0 = max(u, 0), i1 = min(i0 + 1, p.h - 1);
-            if (u_prev == -2) {
-                hrow(i0 - ua, tt, ttl);
-                hrow(i1 - ua, tb, tbl);
-            } else if (u_prev >= 0) {                                // u_prev == -1: same (row 0, row 1) pair again
-                #pragma unroll
-                for (int q = 0; q < NP; ++q) tt[q] = tb[q];
-                ttl = tbl;
-                hrow(i1 - ua, tb, tbl);
-            }
-            u_prev = u;
+            const int cnt = TP::count(u, p.h);
+            const int o0 = (i0 - ua) * G::BW, o1 = (i1 - ua) * G::BW;
+            const int cj0 = j0 - jO, cj1 = j1 - jO;
+            long long px = ((long long)b * p.H + TP::first(u)) * p.W + X;
             float nanflag = 0.f;
             if (!SOFTMAX) {
                 #pragma unroll
-                for (int q = 0; q < NP; ++q) nanflag = __fmaf_rn(tb[q].x + tb[q].y, 0.f, __fmaf_rn(tt[q].x + tt[q].y, 0.f, nanflag));
-                if (G::ODD) nanflag = __fmaf_rn(tbl, 0.f, __fmaf_rn(ttl, 0.f, nanflag));
+                for (int q = 0; q < NP; ++q) nanflag = __fmaf_rn(bot[q].x + bot[q].y, 0.f, __fmaf_rn(top[q].x + top[q].y, 0.f, nanflag));
+                if (G::ODD) nanflag = __fmaf_rn(botl, 0.f, __fmaf_rn(topl, 0.f, nanflag));
             }
-
-            const int cnt = TP::count(u, p.h);
-            const int y0 = TP::first(u);
-            #pragma unroll
-            for (int r = 0; r < S; ++r) {
-                if (r < cnt) {                                       // uniform
-                    const float lh1 = u < 0 ? 0.0f : ((float)r + 0.5f) * (1.0f / S);
-                    const float lh0 = 1.0f - lh1;
-                    const float2 lh0_2 = splat(lh0), lh1_2 = splat(lh1);
-                    float2 z[NP > 0 ? NP : 1];
-                    float zl = 0.f;
+            #pragma unroll 1
+            for (int r = 0; r < cnt; ++r, px += p.W, labs >>= 8) {
+                const float lh1 = u < 0 ? 0.0f : ((float)r + 0.5f) * (1.0f / S);
+                const float lh0 = 1.0f - lh1;
+                const float2 lh0_2 = splat(lh0), lh1_2 = splat(lh1);
+                float2 z[NP > 0 ? NP : 1];
+                float zl = 0.f;
+                #pragma unroll
+                for (int q = 0; q < NP; ++q) z[q] = rnd2<LT>(lerp2_pinned(top[q], lh0_2, bot[q], lh1_2));
+                if (G::ODD) zl = Logit<LT>::rnd(lerp_pinned(topl, lh0, botl, lh1));
+                // max as a 3-input tree (FMNMX3), then the lowest index that attains it (first-max rule of torch.argmax)
+                float m = G::ODD ? zl : z[NP - 1].y;
+                #pragma unroll
+                for (int q = 0; q < NP; ++q) m = fmaxf(m, fmaxf(z[q].x, z[q].y));
+                int idx = C - 1;
+                #pragma unroll
+                for (int q = NP - 1; q >= 0; --q) {
+                    idx = (z[q].y == m) ? 2 * q + 1 : idx;
+                    idx = (z[q].x == m) ? 2 * q : idx;
+                }
+                float ssum = 1.f;
+                const float m2 = __fmul_rn(m, kLog2e);
+                if (SOFTMAX) {
+                    const float2 nm2 = splat(-m2);
+                    float2 a2 = make_float2(0.f, 0.f), b2 = make_float2(0.f, 0.f);
                     #pragma unroll
-                    for (int q = 0; q < NP; ++q) z[q] = rnd2<LT>(lerp2_pinned(tt[q], lh0_2, tb[q], lh1_2));
-                    if (G::ODD) zl = Logit<LT>::rnd(lerp_pinned(ttl, lh0, tbl, lh1));
-                    // first-max argmax
-                    float m; int idx = 0;
-                    if (NP > 0) {
-                        m = z[0].x;
-                        if (z[0].y > m) { m = z[0].y; idx = 1; }
-                        #pragma unroll
-                        for (int q = 1; q < NP; ++q) {
-                            if (z[q].x > m) { m = z[q].x; idx = 2 * q; }
-                            if (z[q].y > m) { m = z[q].y; idx = 2 * q + 1; }
-                        }
-                        if (G::ODD && zl > m) { m = zl; idx = C - 1; }
-                    } else {
-                        m = zl;
+                    for (int q = 0; q < NP; ++q) {
+                        const float2 e = __ffma2_rn(z[q], l2e2, nm2);
+                        const float2 ex = make_float2(ex2_approx(e.x), ex2_approx(e.y));
+                        if (q & 1) b2 = __fadd2_rn(b2, ex); else a2 = __fadd2_rn(a2, ex);
                     }
-                    float ssum = 1.f;
-                    const float m2 = __fmul_rn(m, kLog2e);
-                    if (SOFTMAX) {
-                        const float2 nm2 = splat(-m2);
-                        float2 a2 = make_float2(0.f, 0.f);
-                        #pragma unroll
-                        for (int q = 0; q < NP; ++q) {
-                            const float2 e = __ffma2_rn(z[q], l2e2, nm2);
-                            a2 = __fadd2_rn(a2, make_float2(ex2_approx(e.x), ex2_approx(e.y)));
-                        }
-                        ssum = a2.x + a2.y;
-                        if (G::ODD) ssum += ex2_approx(__fmaf_rn(zl, kLog2e, -m2));
-                    }
-                    const bool weird = SOFTMAX ? (ssum != ssum) : (nanflag != nanflag);
-                    if (weird) {                                     // torch: NaN beats everything, first NaN wins
-                        #pragma unroll 1
-                        for (int k = C - 1; k >= 0; --k) {
-                            const LT* qa = Sg + k * G::PLANE + (i0 - ua) * G::BW;
-                            const LT* qb = Sg + k * G::PLANE + (i1 - ua) * G::BW;
-                            const float t0 = lerp_pinned(Logit<LT>::ld(qa + (j0 - jO)), lw0, Logit<LT>::ld(qa + (j1 - jO)), lw1);
-                            const float t1 = lerp_pinned(Logit<LT>::ld(qb + (j0 - jO)), lw0, Logit<LT>::ld(qb + (j1 - jO)), lw1);
-                            const float zk = Logit<LT>::rnd(lerp_pinned(t0, lh0, t1, lh1));
-                            if (zk != zk) idx = k;
-                        }
-                    }
-                    const int Y = y0 + r;
-                    const long long px = ((long long)b * p.H + Y) * p.W + X;
-                    if (SOFTMAX && colok) {
-                        const float corr = __fmaf_rn(m, kLog2e, -m2);      // exact residual of rn(m*log2e)
-                        const float lg = (__log2f(ssum) - corr) * kLn2;
-                        float l = 0.f;
-                        if (lab[r] >= 0) {
-                            // label logit: same ops, same bits as the z[] entry of that channel
-                            const LT* qa = Sg + lab[r] * G::PLANE + (i0 - ua) * G::BW;
-                            const LT* qb = Sg + lab[r] * G::PLANE + (i1 - ua) * G::BW;
-                            const float t0 = lerp_pinned(Logit<LT>::ld(qa + (j0 - jO)), lw0, Logit<LT>::ld(qa + (j1 - jO)), lw1);
-                            const float t1 = lerp_pinned(Logit<LT>::ld(qb + (j0 - jO)), lw0, Logit<LT>::ld(qb + (j1 - jO)), lw1);
-                            const float zy = Logit<LT>::rnd(lerp_pinned(t0, lh0, t1, lh1));
-                            const float wy = p.class_w ? __ldg(p.class_w + lab[r]) : 1.f;
-                            l = wy * (lg - (zy - m));
-                            tile_loss += l; tile_w += wy; ++cnt_valid;
-                            if (l > p.thresh) { tile_hard += l; ++cnt_hard; }
-                        }
-                        if (p.loss_px) p.loss_px[px] = l;
-                        if (p.lse_px) p.lse_px[px] = m + lg;
-                    }
-                    if (want_hist) {
-                        const int key = (colok && lab[r] >= 0) ? lab[r] * C + idx : -1;
-                        const unsigned peers = __match_any_sync(0xffffffffu, key);
-                        if (key >= 0 && (int)(tid & 31) == __ffs(peers) - 1) atomicAdd(&hist_s[key], __popc(peers));
+                    a2 = __fadd2_rn(a2, b2);
+                    ssum = a2.x + a2.y;
+                    if (G::ODD) ssum += ex2_approx(__fmaf_rn(zl, kLog2e, -m2));
+                }
+                const bool weird = SOFTMAX ? (ssum != ssum) : (nanflag != nanflag);
+                if (weird) {                                         // torch: NaN beats everything, first NaN wins
+                    #pragma unroll 1
+                    for (int k = C - 1; k >= 0; --k) {
+                        const LT* qk = Sg + k * G::PLANE;
+                        const float t0 = lerp_pinned(Logit<LT>::ld(qk + o0 + cj0), lw0, Logit<LT>::ld(qk + o0 + cj1), lw1);
+                        const float t1 = lerp_pinned(Logit<LT>::ld(qk + o1 + cj0), lw0, Logit<LT>::ld(qk + o1 + cj1), lw1);
+                        const float zk = Logit<LT>::rnd(lerp_pinned(t0, lh0, t1, lh1));
+                        if (zk != zk) idx = k;
                     }
                 }
+                const int lab = (int)(labs & 0xffu);
+                const bool valid = lab != 255;
+                if (SOFTMAX && colok) {
+                    const float corr = __fmaf_rn(m, kLog2e, -m2);          // exact residual of rn(m*log2e)
+                    const float lg = (__log2f(ssum) - corr) * kLn2;
+                    float l = 0.f;
+                    if (valid) {
+                        // label logit: same ops, same bits as the z[] entry of that channel
+                        const LT* qk = Sg + lab * G::PLANE;
+                        const float t0 = lerp_pinned(Logit<LT>::ld(qk + o0 + cj0), lw0, Logit<LT>::ld(qk + o0 + cj1), lw1);
+                        const float t1 = lerp_pinned(Logit<LT>::ld(qk + o1 + cj0), lw0, Logit<LT>::ld(qk + o1 + cj1), lw1);
+                        const float zy = Logit<LT>::rnd(lerp_pinned(t0, lh0, t1, lh1));
+                        const float wy = p.class_w ? __ldg(p.class_w + lab) : 1.f;
+                        l = wy * (lg - (zy - m));
+                        tile_loss += l; tile_w += wy; ++cnt_valid;
+                        if (l > p.thresh) { tile_hard += l; ++cnt_hard; }
+                    }
+                    if (p.loss_px) p.loss_px[px] = l;
+                    if (p.lse_px) p.lse_px[px] = m + lg;
+                }
+                if (want_hist) {
+                    const int key = (colok && valid) ? lab * C + idx : -1;
+                    const unsigned peers = __match_any_sync(0xffffffffu, key);
+                    if (key >= 0 && (int)(tid & 31) == __ffs(peers) - 1) atomicAdd(&hist_s[key], __popc(peers));
+                }
+            }
+        };
+
+        // strip walk, two groups per iteration so the bottom row of one group becomes the top row of the next
+        // by swapping the roles of ta/tb (no register copies)
+        int u = u_first;
+        const int u_end = min(u_first + G::GPS, p.h);                // exclusive; uniform per warp (a warp shares sy)
+        if (u < u_end) {
+            const int i0 = max(u, 0), i1 = min(i0 + 1, p.h - 1);
+            hrow(i0 - ua, ta, tal);
+            hrow(i1 - ua, tb, tbl);
+            if (u < 0) {                                             // rim group u = -1 shares (row 0, row 1) with u = 0
+                const unsigned long long labs = pack_labels();
+                fetch_labels(u + 1);
+                do_group(u, ta, tal, tb, tbl, labs);
+                ++u;
+            }
+        }
+        while (u < u_end) {
+            {
+                const unsigned long long labs = pack_labels();
+                fetch_labels(u + 1 < u_end ? u + 1 : p.h);
+                do_group(u, ta, tal, tb, tbl, labs);
+                ++u;
+            }
+            if (u >= u_end) break;
+            {
+                const int i1 = min(u + 1, p.h - 1);
+                hrow(i1 - ua, ta, tal);                              // ta: new bottom row, tb: top row
+                const unsigned long long labs = pack_labels();
+                fetch_labels(u + 1 < u_end ? u + 1 : p.h);
+                do_group(u, tb, tbl, ta, tal, labs);
+                ++u;
+            }
+            if (u >= u_end) break;
+            {
+                const int i1 = min(u + 1, p.h - 1);
+                hrow(i1 - ua, tb, tbl);                              // roles back: ta top, tb bottom
             }
         }
         acc_loss += (double)tile_loss; acc_w += (double)tile_w; acc_hard += (double)tile_hard;
