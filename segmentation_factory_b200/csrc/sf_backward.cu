@@ -271,6 +271,10 @@ int launch_backward(const BwdArgs& a) {
     if (((uintptr_t)a.logits % esz) || ((uintptr_t)a.grad_logits % esz) ||
         (a.ydtype == SF_I64 && ((uintptr_t)a.labels % 8))) return SF_ERR_ALIGN;
 
+    if (!env_no_fast()) {
+        const int rc = launch_backward_fast(a);                    // integer-scale specialisation (sf_backward_fast.cu)
+        if (rc != -1000) return rc;
+    }
     BwdParams p{};
     p.logits = a.logits; p.labels = a.labels; p.class_w = a.class_w; p.loss_px = a.loss_px; p.lse_px = a.lse_px;
     p.grad_out = a.grad_out; p.ws = reinterpret_cast<const Workspace*>(a.ws); p.grad = a.grad_logits;

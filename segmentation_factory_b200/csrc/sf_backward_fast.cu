@@ -1,0 +1,328 @@
+// sf_backward_fast.cu -- integer-scale specialisation of the gather-form fused backward.
+//
+// Same contract as sf_backward.cu; used when H == S*h, W == S*w, S in {4,8} and C is an instantiated class
+// count.  Measured motivation (profiles/r01_v1_*): the generic kernel spent 28% of its instructions in the
+// table-driven horizontal gather, 15% in address arithmetic and stalled on un-prefetched label/loss loads.
+// Schedule of this kernel:
+//   * tile = TH x (256/S - 1) low-res elements x all C channels; its 256 threads are the 256 label columns that
+//     interpolate from the tile's columns (thread t -> cell t/S, phase t%S), walking the S*TH + S dependant rows;
+//   * vertical part in registers, packed fp32x2 over channel pairs: acc_top/acc_bot += p * (coef*lh0 / coef*lh1);
+//     when the walk leaves source row i the finished accumulator is "emitted" and the two accumulator sets swap
+//     roles (no copies), likewise for the horizontal lerps of the staged logits;
+//   * emission: R[k][t] -> shared memory (one conflict-free STS per channel), one __syncthreads, then every owned
+//     (j, k) sums its 2S dependants -- a contiguous, 16-byte aligned run R[k][S*jl .. S*jl + 2S) read with
+//     LDS.128 -- against 2S constant weights held in registers; stores run along j (coalesced);
+//   * label / lse / loss of the next row are prefetched while the current row is computed;
+//   * rows in which no lane of a warp holds a kept pixel skip the channel loop (ignored labels, OHEM drops).
+#include "sf_fast.cuh"
+#include "sf_launch.h"
+
+namespace sf {
+
+constexpr int kBfThreads = 256;
+constexpr int kBfTH = 8;                       // owned low-res rows per tile
+constexpr int kBfBH = kBfTH + 2;               // staged source rows: ia-1 .. ia+TH
+
+struct BfParams {
+    const void* labels;
+    const float* class_w;
+    const float* loss_px;
+    const float* lse_px;
+    const float* grad_out;
+    const Workspace* ws;
+    void* grad;
+    int B, h, w, H, W, ignore, label_u8;
+    int tiles_x, tiles_y;
+};
+
+template <typename LT, int C, int S>
+struct BfGeom {
+    static constexpr int TBW = kBfThreads / S - 1;                  // owned low-res columns per tile
+    static constexpr int XAL = 16 / (int)sizeof(LT);
+    static constexpr int BW = round_up(XAL - 1 + TBW + 2, XAL);     // box cols: floor_al(ja-1) .. ja+TBW
+    static constexpr int PLANE = kBfBH * BW;
+    static constexpr int SRC_BYTES = round_up(C * PLANE * (int)sizeof(LT), 128);
+    static constexpr int NP = C / 2;
+    static constexpr bool ODD = (C & 1) != 0;
+    static constexpr int KQ = kBfThreads / 64;                      // channel phases of the gather (threads / 64)
+};
+
+template <int C>
+__device__ __forceinline__ void onehot_sub2(int y, float2 (&a0)[C / 2 > 0 ? C / 2 : 1], float& a0l,
+                                            float2 (&a1)[C / 2 > 0 ? C / 2 : 1], float& a1l, float v0, float v1) {
+#define SF_CASE(K)                                                                      \
+    case K:                                                                             \
+        if ((K) < (C / 2) * 2) {                                                        \
+            if ((K) & 1) { a0[(K) / 2 < C / 2 ? (K) / 2 : 0].y -= v0; a1[(K) / 2 < C / 2 ? (K) / 2 : 0].y -= v1; } \
+            else         { a0[(K) / 2 < C / 2 ? (K) / 2 : 0].x -= v0; a1[(K) / 2 < C / 2 ? (K) / 2 : 0].x -= v1; } \
+        } else if ((K) == C - 1) { a0l -= v0; a1l -= v1; }                              \
+        break;
+    switch (y) {
+        SF_CASE(0) SF_CASE(1) SF_CASE(2) SF_CASE(3) SF_CASE(4) SF_CASE(5) SF_CASE(6) SF_CASE(7)
+        SF_CASE(8) SF_CASE(9) SF_CASE(10) SF_CASE(11) SF_CASE(12) SF_CASE(13) SF_CASE(14) SF_CASE(15)
+        SF_CASE(16) SF_CASE(17) SF_CASE(18) SF_CASE(19) SF_CASE(20) SF_CASE(21) SF_CASE(22) SF_CASE(23)
+        default: break;
+    }
+#undef SF_CASE
+}
+
+template <typename LT, int C, int S>
+__global__ void __launch_bounds__(kBfThreads, 2)
+bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
+    static_assert(C <= 24, "onehot_sub2 covers 24 classes");
+    using G = BfGeom<LT, C, S>;
+    using TP = ScaleTap<S>;
+    constexpr int NP = G::NP;
+    constexpr int NPA = NP > 0 ? NP : 1;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const LT* Sg = reinterpret_cast<const LT*>(smem);
+    float* Rbuf = reinterpret_cast<float*>(smem + G::SRC_BYTES);                // [2][C][256]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + G::SRC_BYTES + 2 * C * kBfThreads * 4);
+
+    const int tid = threadIdx.x;
+    int bid = blockIdx.x;
+    const int txi = bid % p.tiles_x; bid /= p.tiles_x;
+    const int tyi = bid % p.tiles_y;
+    const int b = bid / p.tiles_y;
+    const int ia = tyi * kBfTH, ib = min(ia + kBfTH, p.h);
+    const int ja = txi * G::TBW, jb = min(ja + G::TBW, p.w);
+    const int nown = jb - ja;
+    const int jO = (ja - 1) & ~(G::XAL - 1);                        // box x-origin: 16-byte aligned, -XAL for the first tile
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(bar, (uint32_t)(C * G::PLANE * (int)sizeof(LT)));
+        tma_load_3d(smem, &tmap, bar, jO, ia - 1, b * C);
+    }
+
+    // ---- this thread's label column ----
+    const int X = S * ja - S / 2 + tid;
+    const bool colok = X >= 0 && X < p.W;
+    int j0, j1; float lw0, lw1;
+    TP::get(min(max(X, 0), p.W - 1), p.w, j0, j1, lw0, lw1);      // idle threads keep an in-box column
+    const LT* c0p = Sg + (j0 - jO);
+    const LT* c1p = Sg + (j1 - jO);
+    const float2 lw0_2 = splat(lw0), lw1_2 = splat(lw1);
+
+    // ---- gather role: owned column jl = tid % 64, channels kq, kq+KQ, ...; 2S constant weights ----
+    const int jl = tid & 63, kq = tid >> 6;
+    const bool gat = jl < nown;
+    float wgt[2 * S];
+    {
+        const int j = ja + jl;
+        #pragma unroll
+        for (int d = 0; d < 2 * S; ++d) {
+            float v = d < S ? ((float)d + 0.5f) * (1.0f / S) : 1.0f - ((float)(d - S) + 0.5f) * (1.0f / S);
+            if (j == 0 && d < S) v = d >= S / 2 ? 1.0f : 0.0f;                    // clamped left rim: l0 = 1
+            if (j == p.w - 1 && d >= S) v = d < S + S / 2 ? 1.0f : 0.0f;          // clamped right rim: l0 + l1 = 1
+            wgt[d] = v;
+        }
+    }
+    LT* gbase = reinterpret_cast<LT*>(p.grad) + (((long long)b * C + kq) * p.h) * p.w + ja + jl;
+
+    const sf_loss_state* stp = &p.ws->state;
+    const int branch = stp->branch;
+    const float kth = stp->kth, tie = stp->tie_share;
+    const float gscale = (p.grad_out ? __ldg(p.grad_out) : 1.0f) * stp->inv_denom;
+    const float2 l2e2 = splat(kLog2e);
+
+    // ---- row walk state ----
+    const int Ya = TP::first(ia - 1 < -1 ? -1 : ia - 1);
+    const int Yb = ib >= p.h ? p.H : TP::first(ib);                // exclusive
+    long long nraw = -1; float nlse = 0.f, nloss = 0.f;            // prefetched inputs of the next row
+    auto prefetch = [&](int Y) {
+        nraw = -1; nlse = 0.f; nloss = 0.f;
+        if (colok && Y < Yb) {
+            const long long px = ((long long)b * p.H + Y) * p.W + X;
+            nraw = ld_label(p.labels, p.label_u8, px);
+            nlse = __ldg(p.lse_px + px);
+            if (branch != 0) nloss = __ldg(p.loss_px + px);
+        }
+    };
+    prefetch(Ya);
+
+    float2 ta[NPA], tb[NPA], accA[NPA], accB[NPA];
+    float tal = 0.f, tbl = 0.f, accAl = 0.f, accBl = 0.f;
+    #pragma unroll
+    for (int q = 0; q < NPA; ++q) { accA[q] = make_float2(0.f, 0.f); accB[q] = make_float2(0.f, 0.f); }
+    auto hrow = [&](int row, float2 (&t)[NPA], float& tl) {
+        const LT* q0 = c0p + row * G::BW;
+        const LT* q1 = c1p + row * G::BW;
+        #pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            const float2 a = make_float2(Logit<LT>::ld(q0 + (2 * q) * G::PLANE), Logit<LT>::ld(q0 + (2 * q + 1) * G::PLANE));
+            const float2 c = make_float2(Logit<LT>::ld(q1 + (2 * q) * G::PLANE), Logit<LT>::ld(q1 + (2 * q + 1) * G::PLANE));
+            t[q] = lerp2_pinned(a, lw0_2, c, lw1_2);
+        }
+        if (G::ODD) tl = lerp_pinned(Logit<LT>::ld(q0 + (C - 1) * G::PLANE), lw0, Logit<LT>::ld(q1 + (C - 1) * G::PLANE), lw1);
+    };
+
+    int ecount = 0;
+    // emit the finished source row i held in `acc`, then clear it.  Called uniformly by all threads.
+    auto emit_row = [&](int i, float2 (&acc)[NPA], float& accl) {
+        if (i >= ia) {
+            float* buf = Rbuf + (ecount & 1) * C * kBfThreads;
+            ++ecount;
+            #pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                buf[(2 * q) * kBfThreads + tid] = acc[q].x;
+                buf[(2 * q + 1) * kBfThreads + tid] = acc[q].y;
+            }
+            if (G::ODD) buf[(C - 1) * kBfThreads + tid] = accl;
+            __syncthreads();
+            if (gat) {
+                LT* g = gbase + (long long)i * p.w;
+                const float* rk = buf + kq * kBfThreads + S * jl;
+                #pragma unroll
+                for (int k = 0; k < (C + G::KQ - 1) / G::KQ; ++k) {
+                    if (kq + k * G::KQ < C) {
+                        float sum = 0.f;
+                        #pragma unroll
+                        for (int d4 = 0; d4 < 2 * S; d4 += 4) {
+                            const float4 v = *reinterpret_cast<const float4*>(rk + k * G::KQ * kBfThreads + d4);
+                            sum = fmaf(v.x, wgt[d4], sum); sum = fmaf(v.y, wgt[d4 + 1], sum);
+                            sum = fmaf(v.z, wgt[d4 + 2], sum); sum = fmaf(v.w, wgt[d4 + 3], sum);
+                        }
+                        Logit<LT>::st(g + (long long)k * G::KQ * p.h * p.w, sum);
+                    }
+                }
+            }
+        }
+        #pragma unroll
+        for (int q = 0; q < NPA; ++q) acc[q] = make_float2(0.f, 0.f);
+        accl = 0.f;
+    };
+
+    // one row group u: top/bot = lerped logits of rows i0/i1, at/ab = gradient accumulators of rows i0/i1
+    auto do_group = [&](int u, const float2 (&top)[NPA], float topl, const float2 (&bot)[NPA], float botl,
+                        float2 (&at)[NPA], float& atl, float2 (&ab)[NPA], float& abl) {
+        const int cnt = TP::count(u, p.h);
+        const int y0 = TP::first(u);
+        const bool merge = u == p.h - 1;                             // i1 == i0: both parts land in row h-1
+        #pragma unroll 1
+        for (int r = 0; r < cnt; ++r) {
+            const long long raw = nraw; const float lse = nlse, loss = nloss;
+            prefetch(y0 + r + 1);
+            float coef = 0.f;
+            const bool valid = raw != p.ignore && raw >= 0 && raw < C;
+            if (valid) {
+                float keep = 1.f;
+                if (branch != 0) keep = loss > kth ? 1.f : (loss == kth ? tie : 0.f);
+                const float wy = p.class_w ? __ldg(p.class_w + raw) : 1.f;
+                coef = keep != 0.f ? keep * wy * gscale : 0.f;       // never 0 * inf
+            }
+            if (__any_sync(0xffffffffu, coef != 0.f)) {
+                if (coef != 0.f) {
+                    const float lh1 = u < 0 ? 0.0f : ((float)r + 0.5f) * (1.0f / S);
+                    const float lh0 = 1.0f - lh1;
+                    const float lse2 = __fmul_rn(lse, kLog2e);
+                    const float corr = __fmaf_rn(lse, kLog2e, -lse2);        // exact residual of rn(lse*log2e)
+                    const float cf = coef * __fmaf_rn(-corr, kLn2, 1.0f);    // 2^-corr to first order
+                    float v0 = cf * lh0, v1 = cf * lh1, o0 = coef * lh0, o1 = coef * lh1;
+                    if (merge) { v0 += v1; v1 = 0.f; o0 += o1; o1 = 0.f; }
+                    const float2 lh0_2 = splat(lh0), lh1_2 = splat(lh1), nl2 = splat(-lse2);
+                    const float2 v0_2 = splat(v0), v1_2 = splat(v1);
+                    #pragma unroll
+                    for (int q = 0; q < NP; ++q) {
+                        const float2 z = rnd2<LT>(lerp2_pinned(top[q], lh0_2, bot[q], lh1_2));
+                        const float2 e = __ffma2_rn(z, l2e2, nl2);
+                        const float2 pc = make_float2(ex2_approx(e.x), ex2_approx(e.y));
+                        at[q] = __ffma2_rn(pc, v0_2, at[q]);
+                        ab[q] = __ffma2_rn(pc, v1_2, ab[q]);
+                    }
+                    if (G::ODD) {
+                        const float z = Logit<LT>::rnd(lerp_pinned(topl, lh0, botl, lh1));
+                        const float pc = ex2_approx(__fmaf_rn(z, kLog2e, -lse2));
+                        atl = fmaf(pc, v0, atl);
+                        abl = fmaf(pc, v1, abl);
+                    }
+                    onehot_sub2<C>((int)raw, at, atl, ab, abl, o0, o1);
+                }
+            }
+        }
+    };
+
+    __syncthreads();
+    mbar_wait(bar, 0);
+
+    // ---- walk groups u = ia-1 .. ib-1, two per iteration with swapped roles (no register copies) ----
+    int u = ia - 1;
+    {
+        const int i0 = max(u, 0), i1 = min(i0 + 1, p.h - 1);
+        hrow(i0 - (ia - 1), ta, tal);
+        hrow(i1 - (ia - 1), tb, tbl);
+        if (u < 0) {                                                 // rim group u = -1 shares rows (0, 1) with u = 0
+            do_group(u, ta, tal, tb, tbl, accA, accAl, accB, accBl);
+            ++u;
+        }
+    }
+    while (u < ib) {
+        do_group(u, ta, tal, tb, tbl, accA, accAl, accB, accBl);
+        emit_row(u, accA, accAl);                                    // row u complete; accB now collects row u+1
+        ++u;
+        if (u >= ib) break;
+        hrow(min(u + 1, p.h - 1) - (ia - 1), ta, tal);               // ta: new bottom row
+        do_group(u, tb, tbl, ta, tal, accB, accBl, accA, accAl);
+        emit_row(u, accB, accBl);
+        ++u;
+        if (u >= ib) break;
+        hrow(min(u + 1, p.h - 1) - (ia - 1), tb, tbl);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+template <typename LT, int C, int S>
+static int bf_launch(const BwdArgs& a) {
+    using G = BfGeom<LT, C, S>;
+    if (a.w < G::BW || a.h < kBfBH) return -1000;                   // TMA box must fit inside the tensor
+    BfParams p{};
+    p.labels = a.labels; p.class_w = a.class_w; p.loss_px = a.loss_px; p.lse_px = a.lse_px; p.grad_out = a.grad_out;
+    p.ws = reinterpret_cast<const Workspace*>(a.ws); p.grad = a.grad_logits;
+    p.B = a.B; p.h = a.h; p.w = a.w; p.H = a.H; p.W = a.W; p.ignore = a.ignore; p.label_u8 = a.ydtype == SF_U8;
+    p.tiles_x = (a.w + G::TBW - 1) / G::TBW;
+    p.tiles_y = (a.h + kBfTH - 1) / kBfTH;
+    const long long grid = (long long)a.B * p.tiles_x * p.tiles_y;
+    if (grid >= (1LL << 31)) return SF_ERR_SHAPE;
+    CUtensorMap tmap{};
+    const int rc = make_logits_tmap(&tmap, a.logits, a.ldtype, a.B * C, a.h, a.w, C, kBfBH, G::BW);
+    if (rc != 0) return rc;
+    const size_t smem = (size_t)G::SRC_BYTES + (size_t)2 * C * kBfThreads * 4 + 16;
+    auto k = bwd_fast_kernel<LT, C, S>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    k<<<(int)grid, kBfThreads, smem, reinterpret_cast<cudaStream_t>(a.stream)>>>(tmap, p);
+    return (int)cudaGetLastError();
+}
+
+template <typename LT, int C>
+static int bf_scale(const BwdArgs& a, int s) {
+    switch (s) {
+        case 4: return bf_launch<LT, C, 4>(a);
+        case 8: return bf_launch<LT, C, 8>(a);
+        default: return -1000;
+    }
+}
+template <typename LT>
+static int bf_classes(const BwdArgs& a, int s) {
+    switch (a.C) {
+        case 19: return bf_scale<LT, 19>(a, s);
+        case 21: return bf_scale<LT, 21>(a, s);
+        default: return -1000;
+    }
+}
+
+// Returns -1000 when the shape is not covered (the caller then takes the generic kernel).
+int launch_backward_fast(const BwdArgs& a) {
+    if (a.force_no_tma || a.h <= 0 || a.w <= 0 || a.H % a.h || a.W % a.w) return -1000;
+    const int s = a.H / a.h;
+    if (s != a.W / a.w) return -1000;
+    const int esz = a.ldtype == SF_F32 ? 4 : 2;
+    if (((size_t)a.w * esz) % 16 || ((uintptr_t)a.logits % 16)) return -1000;
+    if (a.ldtype == SF_F32) return bf_classes<float>(a, s);
+    if (a.ldtype == SF_BF16) return bf_classes<__nv_bfloat16>(a, s);
+    return bf_classes<__half>(a, s);
+}
+
+}  // namespace sf

@@ -96,7 +96,7 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
         const int X = Xa + tx;
         const bool colok = X < p.W;
         int j0, j1; float lw0, lw1;
-        TP::get(colok ? X : p.W - 1, p.w, j0, j1, lw0, lw1);
+        TP::get(min(X, p.W - 1), p.w, j0, j1, lw0, lw1);            // idle threads keep an in-box column
         const int jO = Xa / S - G::XAL;
         const LT* Sg = reinterpret_cast<const LT*>(smem + (n % kFfStages) * G::STAGE_BYTES);
         const LT* c0p = Sg + (j0 - jO);                            // column taps inside the box

@@ -37,6 +37,7 @@ struct BwdArgs {
     bool force_no_tma;
 };
 int launch_backward(const BwdArgs& a);
+int launch_backward_fast(const BwdArgs& a);   // -1000: shape not covered
 
 int launch_finalize(const float* loss_px, long long n_px, float thresh, void* ws, float* loss_out, void* stream);
 int launch_hist_pairs(const void* a, int adtype, const long long* b, long long n, int C,
