@@ -78,6 +78,9 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
     const LT* Sg = reinterpret_cast<const LT*>(smem);
     float* Rbuf = reinterpret_cast<float*>(smem + G::SRC_BYTES);                // [2][C][256]
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + G::SRC_BYTES + 2 * C * kBfThreads * 4);
+    __shared__ float cw_s[32];                                      // class weights (1.0 when none): an LDS in the row loop
+                                                                    // instead of an LDG that would share a scoreboard slot
+                                                                    // with the row-ahead prefetch and serialise it
 
     const int tid = threadIdx.x;
     int bid = blockIdx.x;
@@ -88,6 +91,7 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
     const int ja = txi * G::TBW, jb = min(ja + G::TBW, p.w);
     const int nown = jb - ja;
     const int jO = (ja - 1) & ~(G::XAL - 1);                        // box x-origin: 16-byte aligned, -XAL for the first tile
+    if (tid < 32) cw_s[tid] = (p.class_w && tid < C) ? __ldg(p.class_w + tid) : 1.0f;
     if (tid == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
@@ -130,16 +134,19 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
     const int Ya = TP::first(ia - 1 < -1 ? -1 : ia - 1);
     const int Yb = ib >= p.h ? p.H : TP::first(ib);                // exclusive
     long long nraw = -1; float nlse = 0.f, nloss = 0.f;            // prefetched inputs of the next row
-    auto prefetch = [&](int Y) {
+    // running element offset of (b, Y, X); advanced by W per row so the loop carries no 64-bit multiplies
+    long long pxn = ((long long)b * p.H + Ya) * p.W + (colok ? X : 0);
+    int rows_left = colok ? Yb - Ya : 0;
+    auto prefetch = [&]() {
         nraw = -1; nlse = 0.f; nloss = 0.f;
-        if (colok && Y < Yb) {
-            const long long px = ((long long)b * p.H + Y) * p.W + X;
-            nraw = ld_label(p.labels, p.label_u8, px);
-            nlse = __ldg(p.lse_px + px);
-            if (branch != 0) nloss = __ldg(p.loss_px + px);
+        if (rows_left > 0) {
+            nraw = ld_label(p.labels, p.label_u8, pxn);
+            nlse = __ldg(p.lse_px + pxn);
+            if (branch != 0) nloss = __ldg(p.loss_px + pxn);
         }
+        pxn += p.W; --rows_left;
     };
-    prefetch(Ya);
+    prefetch();
 
     float2 ta[NPA], tb[NPA], accA[NPA], accB[NPA];
     float tal = 0.f, tbl = 0.f, accAl = 0.f, accBl = 0.f;
@@ -197,18 +204,20 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
     auto do_group = [&](int u, const float2 (&top)[NPA], float topl, const float2 (&bot)[NPA], float botl,
                         float2 (&at)[NPA], float& atl, float2 (&ab)[NPA], float& abl) {
         const int cnt = TP::count(u, p.h);
-        const int y0 = TP::first(u);
         const bool merge = u == p.h - 1;                             // i1 == i0: both parts land in row h-1
+        // "- onehot" part: consecutive rows of a column mostly share their label, so its two sums are kept as a
+        // run and applied to the label's accumulator lane (a 24-way switch) only when the label changes
+        int run_y = -1; float run0 = 0.f, run1 = 0.f;
         #pragma unroll 1
         for (int r = 0; r < cnt; ++r) {
             const long long raw = nraw; const float lse = nlse, loss = nloss;
-            prefetch(y0 + r + 1);
+            prefetch();
             float coef = 0.f;
             const bool valid = raw != p.ignore && raw >= 0 && raw < C;
             if (valid) {
                 float keep = 1.f;
                 if (branch != 0) keep = loss > kth ? 1.f : (loss == kth ? tie : 0.f);
-                const float wy = p.class_w ? __ldg(p.class_w + raw) : 1.f;
+                const float wy = cw_s[(int)raw];
                 coef = keep != 0.f ? keep * wy * gscale : 0.f;       // never 0 * inf
             }
             if (__any_sync(0xffffffffu, coef != 0.f)) {
@@ -236,10 +245,15 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
                         atl = fmaf(pc, v0, atl);
                         abl = fmaf(pc, v1, abl);
                     }
-                    onehot_sub2<C>((int)raw, at, atl, ab, abl, o0, o1);
+                    if ((int)raw != run_y) {
+                        if (run_y >= 0) onehot_sub2<C>(run_y, at, atl, ab, abl, run0, run1);
+                        run_y = (int)raw; run0 = 0.f; run1 = 0.f;
+                    }
+                    run0 += o0; run1 += o1;
                 }
             }
         }
+        if (run_y >= 0) onehot_sub2<C>(run_y, at, atl, ab, abl, run0, run1);
     };
 
     __syncthreads();

@@ -54,9 +54,11 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
     int* hist_s = reinterpret_cast<int*>(smem + kFfStages * G::STAGE_BYTES);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + kFfStages * G::STAGE_BYTES + round_up(C * C * 4, 16));
     __shared__ double red_scratch[kFfThreads / 32];
-
+    __shared__ float cw_s[32];                                      // class weights as LDS: an LDG in the row loop would share
+                                                                    // a scoreboard slot with the label prefetch and serialise it
     const int tid = threadIdx.x;
     const int tx = tid % kFfTW, sy = tid / kFfTW;
+    if (tid < 32) cw_s[tid] = (p.class_w && tid < C) ? __ldg(p.class_w + tid) : 1.0f;
     const bool want_hist = p.hist != nullptr;
 
     if (want_hist)
@@ -220,7 +222,7 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
                         const float t0 = lerp_pinned(Logit<LT>::ld(qk + o0 + cj0), lw0, Logit<LT>::ld(qk + o0 + cj1), lw1);
                         const float t1 = lerp_pinned(Logit<LT>::ld(qk + o1 + cj0), lw0, Logit<LT>::ld(qk + o1 + cj1), lw1);
                         const float zy = Logit<LT>::rnd(lerp_pinned(t0, lh0, t1, lh1));
-                        const float wy = p.class_w ? __ldg(p.class_w + lab) : 1.f;
+                        const float wy = cw_s[lab];
                         l = wy * (lg - (zy - m));
                         tile_loss += l; tile_w += wy; ++cnt_valid;
                         if (l > p.thresh) { tile_hard += l; ++cnt_hard; }
