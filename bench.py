@@ -251,7 +251,7 @@ def main():
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = algorithmic_bytes_per_px(dom) * n_px / (kern[dom] * 1e-3) / 1e9
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    tp = os.path.join(ROOT, "profiles", "traffic_latest.json")     # dram read+write bytes per launch from ncu --set full
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get(dom)
     roofline = {"bound": "hbm", "kernel": f"sf::{dom}_kernel<float,19>", "achieved": achieved, "peak": peak, "unit": "GB/s",
