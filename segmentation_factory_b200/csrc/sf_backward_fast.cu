@@ -133,20 +133,29 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
     // ---- row walk state ----
     const int Ya = TP::first(ia - 1 < -1 ? -1 : ia - 1);
     const int Yb = ib >= p.h ? p.H : TP::first(ib);                // exclusive
-    long long nraw = -1; float nlse = 0.f, nloss = 0.f;            // prefetched inputs of the next row
-    // running element offset of (b, Y, X); advanced by W per row so the loop carries no 64-bit multiplies
-    long long pxn = ((long long)b * p.H + Ya) * p.W + (colok ? X : 0);
-    int rows_left = colok ? Yb - Ya : 0;
+    // Prefetched inputs of the next row (label as two 32-bit halves), fetched through running pointers so the
+    // row loop carries no 64-bit multiplies; `live` counts the rows this column still has to consume.
+    int nlo = -1, nhi = -1; float nlse = 0.f, nloss = 0.f;
+    const bool has_loss = branch != 0;
+    const long long px0 = ((long long)b * p.H + Ya) * p.W + (colok ? X : 0);
+    const char* lab_p = reinterpret_cast<const char*>(p.labels) + px0 * (p.label_u8 ? 1 : 8);
+    const float* lse_p = p.lse_px + px0;
+    const float* loss_p = (has_loss ? p.loss_px : p.lse_px) + px0;
+    const long long lab_step = (long long)p.W * (p.label_u8 ? 1 : 8);
+    int to_fetch = colok ? Yb - Ya : 0;
+    int live = to_fetch;
     auto prefetch = [&]() {
-        nraw = -1; nlse = 0.f; nloss = 0.f;
-        if (rows_left > 0) {
-            nraw = ld_label(p.labels, p.label_u8, pxn);
-            nlse = __ldg(p.lse_px + pxn);
-            if (branch != 0) nloss = __ldg(p.loss_px + pxn);
+        if (to_fetch > 0) {
+            if (p.label_u8) { nlo = (int)__ldg(reinterpret_cast<const unsigned char*>(lab_p)); nhi = 0; }
+            else { const int2 t = __ldg(reinterpret_cast<const int2*>(lab_p)); nlo = t.x; nhi = t.y; }
+            nlse = __ldg(lse_p);
+            if (has_loss) nloss = __ldg(loss_p);
         }
-        pxn += p.W; --rows_left;
+        lab_p += lab_step; lse_p += p.W; loss_p += p.W; --to_fetch;
     };
     prefetch();
+    const int ign = p.ignore;
+    const float inv_s = 1.0f / S;
 
     float2 ta[NPA], tb[NPA], accA[NPA], accB[NPA];
     float tal = 0.f, tbl = 0.f, accAl = 0.f, accBl = 0.f;
@@ -208,27 +217,28 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
         // "- onehot" part: consecutive rows of a column mostly share their label, so its two sums are kept as a
         // run and applied to the label's accumulator lane (a 24-way switch) only when the label changes
         int run_y = -1; float run0 = 0.f, run1 = 0.f;
+        float lh1 = u < 0 ? 0.0f : 0.5f * inv_s;                     // (r + 0.5) / S, stepped by 1/S per row
+        const float lh1_step = u < 0 ? 0.0f : inv_s;
         #pragma unroll 1
-        for (int r = 0; r < cnt; ++r) {
-            const long long raw = nraw; const float lse = nlse, loss = nloss;
+        for (int r = 0; r < cnt; ++r, lh1 += lh1_step) {
+            const int lo = nlo, hi = nhi; const float lse = nlse, loss = nloss;
+            const bool alive = live > 0;
+            --live;
             prefetch();
-            float coef = 0.f;
-            const bool valid = raw != p.ignore && raw >= 0 && raw < C;
-            if (valid) {
-                float keep = 1.f;
-                if (branch != 0) keep = loss > kth ? 1.f : (loss == kth ? tie : 0.f);
-                const float wy = cw_s[(int)raw];
-                coef = keep != 0.f ? keep * wy * gscale : 0.f;       // never 0 * inf
-            }
+            // valid label: 0 <= y < C, y != ignore (64-bit labels: high word must be zero)
+            const bool valid = alive && hi == 0 && (unsigned)lo < (unsigned)C && lo != ign;
+            float keep = 1.f;
+            if (has_loss) keep = loss > kth ? 1.f : (loss == kth ? tie : 0.f);
+            const float wy = cw_s[valid ? lo : 0];
+            const float coef = (valid && keep != 0.f) ? keep * wy * gscale : 0.f;     // never 0 * inf
             if (__any_sync(0xffffffffu, coef != 0.f)) {
                 if (coef != 0.f) {
-                    const float lh1 = u < 0 ? 0.0f : ((float)r + 0.5f) * (1.0f / S);
                     const float lh0 = 1.0f - lh1;
                     const float lse2 = __fmul_rn(lse, kLog2e);
                     const float corr = __fmaf_rn(lse, kLog2e, -lse2);        // exact residual of rn(lse*log2e)
                     const float cf = coef * __fmaf_rn(-corr, kLn2, 1.0f);    // 2^-corr to first order
-                    float v0 = cf * lh0, v1 = cf * lh1, o0 = coef * lh0, o1 = coef * lh1;
-                    if (merge) { v0 += v1; v1 = 0.f; o0 += o1; o1 = 0.f; }
+                    const float aw0 = merge ? 1.0f : lh0, aw1 = merge ? 0.0f : lh1;   // clamped last row: l0 + l1 = 1
+                    const float v0 = cf * aw0, v1 = cf * aw1, o0 = coef * aw0, o1 = coef * aw1;
                     const float2 lh0_2 = splat(lh0), lh1_2 = splat(lh1), nl2 = splat(-lse2);
                     const float2 v0_2 = splat(v0), v1_2 = splat(v1);
                     #pragma unroll
@@ -245,9 +255,9 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
                         atl = fmaf(pc, v0, atl);
                         abl = fmaf(pc, v1, abl);
                     }
-                    if ((int)raw != run_y) {
+                    if (lo != run_y) {
                         if (run_y >= 0) onehot_sub2<C>(run_y, at, atl, ab, abl, run0, run1);
-                        run_y = (int)raw; run0 = 0.f; run1 = 0.f;
+                        run_y = lo; run0 = 0.f; run1 = 0.f;
                     }
                     run0 += o0; run1 += o1;
                 }
