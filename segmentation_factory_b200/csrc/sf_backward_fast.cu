@@ -33,6 +33,7 @@ struct BfParams {
     void* grad;
     int B, h, w, H, W, ignore, label_u8;
     int tiles_x, tiles_y;
+    int Ctot, n_chunks;                         // chunked mode: classes in the tensor, CTAs per tile along channels
 };
 
 template <typename LT, int C, int S>
@@ -66,7 +67,10 @@ __device__ __forceinline__ void onehot_sub2(int y, float2 (&a0)[C / 2 > 0 ? C / 
 #undef SF_CASE
 }
 
-template <typename LT, int C, int S>
+// C = channels handled by one CTA.  CHUNK = false: C is the class count.  CHUNK = true: the classes are split into
+// ceil(Ctot / C) chunks, one CTA per (tile, chunk) -- chunks are independent in the backward because the softmax
+// denominator arrives as lse_px; label/lse/loss are re-read per chunk (L2 hits: the chunk index varies fastest).
+template <typename LT, int C, int S, bool CHUNK>
 __global__ void __launch_bounds__(kBfThreads, 2)
 bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
     static_assert(C <= 24, "onehot_sub2 covers 24 classes");
@@ -78,12 +82,17 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
     const LT* Sg = reinterpret_cast<const LT*>(smem);
     float* Rbuf = reinterpret_cast<float*>(smem + G::SRC_BYTES);                // [2][C][256]
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + G::SRC_BYTES + 2 * C * kBfThreads * 4);
-    __shared__ float cw_s[32];                                      // class weights (1.0 when none): an LDS in the row loop
+    __shared__ float cw_s[CHUNK ? 256 : 32];                        // class weights (1.0 when none): an LDS in the row loop
                                                                     // instead of an LDG that would share a scoreboard slot
                                                                     // with the row-ahead prefetch and serialise it
 
     const int tid = threadIdx.x;
     int bid = blockIdx.x;
+    const int chunk = CHUNK ? bid % p.n_chunks : 0;
+    if (CHUNK) bid /= p.n_chunks;
+    const int Ct = CHUNK ? p.Ctot : C;                              // classes in the tensor
+    const int c0 = chunk * C;                                       // first class of this CTA
+    const int nvalid = CHUNK ? min(C, Ct - c0) : C;
     const int txi = bid % p.tiles_x; bid /= p.tiles_x;
     const int tyi = bid % p.tiles_y;
     const int b = bid / p.tiles_y;
@@ -91,12 +100,12 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
     const int ja = txi * G::TBW, jb = min(ja + G::TBW, p.w);
     const int nown = jb - ja;
     const int jO = (ja - 1) & ~(G::XAL - 1);                        // box x-origin: 16-byte aligned, -XAL for the first tile
-    if (tid < 32) cw_s[tid] = (p.class_w && tid < C) ? __ldg(p.class_w + tid) : 1.0f;
+    if (tid < (CHUNK ? 256 : 32)) cw_s[tid] = (p.class_w && tid < Ct) ? __ldg(p.class_w + tid) : 1.0f;
     if (tid == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
         mbar_expect_tx(bar, (uint32_t)(C * G::PLANE * (int)sizeof(LT)));
-        tma_load_3d(smem, &tmap, bar, jO, ia - 1, b * C);
+        tma_load_3d(smem, &tmap, bar, jO, ia - 1, b * Ct + c0);     // a tail chunk reads past its classes: never stored
     }
 
     // ---- this thread's label column ----
@@ -122,7 +131,7 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
             wgt[d] = v;
         }
     }
-    LT* gbase = reinterpret_cast<LT*>(p.grad) + (((long long)b * C + kq) * p.h) * p.w + ja + jl;
+    LT* gbase = reinterpret_cast<LT*>(p.grad) + (((long long)b * Ct + c0 + kq) * p.h) * p.w + ja + jl;
 
     const sf_loss_state* stp = &p.ws->state;
     const int branch = stp->branch;
@@ -191,7 +200,7 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
                 const float* rk = buf + kq * kBfThreads + S * jl;
                 #pragma unroll
                 for (int k = 0; k < (C + G::KQ - 1) / G::KQ; ++k) {
-                    if (kq + k * G::KQ < C) {
+                    if (kq + k * G::KQ < nvalid) {
                         float sum = 0.f;
                         #pragma unroll
                         for (int d4 = 0; d4 < 2 * S; d4 += 4) {
@@ -226,7 +235,7 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
             --live;
             prefetch();
             // valid label: 0 <= y < C, y != ignore (64-bit labels: high word must be zero)
-            const bool valid = alive && hi == 0 && (unsigned)lo < (unsigned)C && lo != ign;
+            const bool valid = alive && hi == 0 && (unsigned)lo < (unsigned)Ct && lo != ign;
             float keep = 1.f;
             if (has_loss) keep = loss > kth ? 1.f : (loss == kth ? tie : 0.f);
             const float wy = cw_s[valid ? lo : 0];
@@ -255,9 +264,10 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
                         atl = fmaf(pc, v0, atl);
                         abl = fmaf(pc, v1, abl);
                     }
-                    if (lo != run_y) {
+                    const int yk = ((unsigned)(lo - c0) < (unsigned)nvalid) ? lo - c0 : -1;   // label inside this CTA's classes?
+                    if (yk != run_y) {
                         if (run_y >= 0) onehot_sub2<C>(run_y, at, atl, ab, abl, run0, run1);
-                        run_y = lo; run0 = 0.f; run1 = 0.f;
+                        run_y = yk; run0 = 0.f; run1 = 0.f;
                     }
                     run0 += o0; run1 += o1;
                 }
@@ -297,43 +307,45 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
 // ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
-template <typename LT, int C, int S>
+template <typename LT, int C, int S, bool CHUNK>
 static int bf_launch(const BwdArgs& a) {
     using G = BfGeom<LT, C, S>;
     if (a.w < G::BW || a.h < kBfBH) return -1000;                   // TMA box must fit inside the tensor
+    if (CHUNK && a.C > 256) return -1000;
     BfParams p{};
     p.labels = a.labels; p.class_w = a.class_w; p.loss_px = a.loss_px; p.lse_px = a.lse_px; p.grad_out = a.grad_out;
     p.ws = reinterpret_cast<const Workspace*>(a.ws); p.grad = a.grad_logits;
     p.B = a.B; p.h = a.h; p.w = a.w; p.H = a.H; p.W = a.W; p.ignore = a.ignore; p.label_u8 = a.ydtype == SF_U8;
     p.tiles_x = (a.w + G::TBW - 1) / G::TBW;
     p.tiles_y = (a.h + kBfTH - 1) / kBfTH;
-    const long long grid = (long long)a.B * p.tiles_x * p.tiles_y;
+    p.Ctot = a.C; p.n_chunks = CHUNK ? (a.C + C - 1) / C : 1;
+    const long long grid = (long long)a.B * p.tiles_x * p.tiles_y * p.n_chunks;
     if (grid >= (1LL << 31)) return SF_ERR_SHAPE;
     CUtensorMap tmap{};
-    const int rc = make_logits_tmap(&tmap, a.logits, a.ldtype, a.B * C, a.h, a.w, C, kBfBH, G::BW);
+    const int rc = make_logits_tmap(&tmap, a.logits, a.ldtype, a.B * a.C, a.h, a.w, C, kBfBH, G::BW);
     if (rc != 0) return rc;
     const size_t smem = (size_t)G::SRC_BYTES + (size_t)2 * C * kBfThreads * 4 + 16;
-    auto k = bwd_fast_kernel<LT, C, S>;
+    auto k = bwd_fast_kernel<LT, C, S, CHUNK>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     k<<<(int)grid, kBfThreads, smem, reinterpret_cast<cudaStream_t>(a.stream)>>>(tmap, p);
     return (int)cudaGetLastError();
 }
 
-template <typename LT, int C>
+template <typename LT, int C, bool CHUNK>
 static int bf_scale(const BwdArgs& a, int s) {
     switch (s) {
-        case 4: return bf_launch<LT, C, 4>(a);
-        case 8: return bf_launch<LT, C, 8>(a);
+        case 4: return bf_launch<LT, C, 4, CHUNK>(a);
+        case 8: return bf_launch<LT, C, 8, CHUNK>(a);
         default: return -1000;
     }
 }
 template <typename LT>
 static int bf_classes(const BwdArgs& a, int s) {
     switch (a.C) {
-        case 19: return bf_scale<LT, 19>(a, s);
-        case 21: return bf_scale<LT, 21>(a, s);
-        default: return -1000;
+        case 19: return bf_scale<LT, 19, false>(a, s);
+        case 21: return bf_scale<LT, 21, false>(a, s);
+        default: return a.C > 24 ? bf_scale<LT, 16, true>(a, s) : -1000;   // many classes: 16-class chunks
     }
 }
 

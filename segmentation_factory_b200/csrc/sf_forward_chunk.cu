@@ -1,0 +1,340 @@
+// sf_forward_chunk.cu -- integer-scale fused forward for MANY classes (ADE20K 150/151, COCO-Stuff 171/172).
+//
+// Same contract and arithmetic as sf_forward.cu / sf_forward_fast.cu.  With C > 24 the classes no longer fit one
+// thread's registers, so they stream through in chunks of 16 (8 fp32x2 pairs) with an online softmax per pixel:
+// running max m, running sum s of 2^(z*log2e - rn(m*log2e)) (rescaled by the difference of the ROUNDED exponents
+// when m grows, so every term stays relative to one rn(m*log2e)), running first-max index, and the label logit.
+// Work item = (tile, chunk); tile = 64 label columns x 8 row groups (512 threads, one row group of S rows per
+// thread, so the per-pixel state is 4*S registers); box [16][9][BW] per item through a 3-stage TMA/mbarrier ring;
+// persistent CTAs.  Geometry is constexpr (sf_fast.cuh), arithmetic is packed fp32x2, the max is an FMNMX3 tree and
+// the in-chunk index is only recovered for pixels whose running max actually moved.
+// The C x C int32 histogram (90-118 KB for 150-172 classes) shares the SM's shared memory with the ring, hence one
+// 512-thread CTA per SM when the matrix is requested.
+#include "sf_fast.cuh"
+#include "sf_launch.h"
+
+namespace sf {
+
+constexpr int kFcTW = 64, kFcStrips = 8, kFcThreads = kFcTW * kFcStrips, kFcStages = 3, kFcNCH = 16, kFcNP = kFcNCH / 2;
+
+struct FcParams {
+    const void* labels;
+    const float* class_w;
+    float* loss_px;
+    float* lse_px;
+    unsigned long long* hist;
+    Workspace* ws;
+    int B, C, h, w, H, W, ignore, label_u8;
+    float thresh;
+    int tiles_x, tiles_y, total_tiles, n_chunks, hist_bytes;
+};
+
+template <typename LT, int S>
+struct FcGeom {
+    static constexpr int NGT = kFcStrips;                           // row groups per tile (one per thread row)
+    static constexpr int BH = NGT + 1;
+    static constexpr int XAL = 16 / (int)sizeof(LT);
+    static constexpr int BW = round_up(XAL + kFcTW / S + 1, XAL);
+    static constexpr int PLANE = BH * BW;
+    static constexpr int STAGE_BYTES = round_up(kFcNCH * PLANE * (int)sizeof(LT), 128);
+};
+
+template <typename LT, int S, bool SOFTMAX>
+__global__ void __launch_bounds__(kFcThreads, 1)
+fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmap, const FcParams p) {
+    using G = FcGeom<LT, S>;
+    using TP = ScaleTap<S>;
+    constexpr int NP = kFcNP;
+    extern __shared__ __align__(128) unsigned char smem[];
+    int* hist_s = reinterpret_cast<int*>(smem + kFcStages * G::STAGE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kFcStages * G::STAGE_BYTES + p.hist_bytes);
+    __shared__ double red_scratch[kFcThreads / 32];
+    __shared__ float cw_s[256];
+
+    const int tid = threadIdx.x;
+    const int tx = tid % kFcTW, sy = tid / kFcTW;
+    const bool want_hist = p.hist != nullptr;
+    const unsigned lane_lt = (1u << (tid & 31)) - 1u;
+    const int C = p.C;
+
+    if (want_hist)
+        for (int k = tid; k < C * C; k += kFcThreads) hist_s[k] = 0;
+    if (tid < 256) cw_s[tid] = (p.class_w && tid < C) ? __ldg(p.class_w + tid) : 1.0f;
+    if (tid == 0) {
+        tma_prefetch_desc(&tmap);
+        for (int s = 0; s < kFcStages; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int per_img = p.tiles_x * p.tiles_y;
+    int n_tiles = 0;
+    if ((int)blockIdx.x < p.total_tiles) n_tiles = (p.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1;
+    const int n_items = n_tiles * p.n_chunks;
+
+    auto issue = [&](int n) {
+        const int tile = blockIdx.x + (n / p.n_chunks) * gridDim.x;
+        const int chunk = n % p.n_chunks;
+        const int b = tile / per_img, r = tile % per_img;
+        const int ua = -1 + (r / p.tiles_x) * G::NGT;
+        const int jO = (r % p.tiles_x) * (kFcTW / S) - G::XAL;
+        uint64_t* bar = &full[n % kFcStages];
+        mbar_expect_tx(bar, (uint32_t)(kFcNCH * G::PLANE * (int)sizeof(LT)));
+        tma_load_3d(smem + (n % kFcStages) * G::STAGE_BYTES, &tmap, bar, jO, ua, b * C + chunk * kFcNCH);
+    };
+    if (tid == 0)
+        for (int n = 0; n < kFcStages && n < n_items; ++n) issue(n);
+
+    double acc_loss = 0.0, acc_w = 0.0, acc_hard = 0.0;
+    unsigned int cnt_valid = 0, cnt_hard = 0;
+    const float2 l2e2 = splat(kLog2e);
+
+    // per-(tile) thread state
+    int b = 0, ua = 0, X = 0, j0 = 0, j1 = 0, jO = 0, u = 0, cnt = 0, i0 = 0, i1 = 0;
+    float lw0 = 0.f, lw1 = 0.f;
+    bool colok = false;
+    unsigned long long labs = 0;
+    unsigned nanlock = 0;
+    float m[S], s[S], zy[S];
+    int idx[S];
+
+    for (int n = 0; n < n_items; ++n) {
+        const int chunk = n % p.n_chunks;
+        const LT* Sg = reinterpret_cast<const LT*>(smem + (n % kFcStages) * G::STAGE_BYTES);
+
+        if (chunk == 0) {
+            const int tile = blockIdx.x + (n / p.n_chunks) * gridDim.x;
+            b = tile / per_img;
+            const int rr = tile % per_img;
+            ua = -1 + (rr / p.tiles_x) * G::NGT;
+            const int Xa = (rr % p.tiles_x) * kFcTW;
+            X = Xa + tx;
+            colok = X < p.W;
+            TP::get(min(X, p.W - 1), p.w, j0, j1, lw0, lw1);
+            jO = Xa / S - G::XAL;
+            u = ua + sy;
+            cnt = (u <= p.h - 1 && colok) ? TP::count(u, p.h) : 0;
+            i0 = max(u, 0); i1 = min(i0 + 1, p.h - 1);
+            labs = 0; nanlock = 0;
+            #pragma unroll
+            for (int r = 0; r < S; ++r) { m[r] = -INFINITY; s[r] = 0.f; zy[r] = 0.f; idx[r] = 0; }
+            if (cnt > 0) {
+                const long long base = ((long long)b * p.H + TP::first(u)) * p.W + X;
+                #pragma unroll
+                for (int r = 0; r < S; ++r) {
+                    unsigned v = 255u;
+                    if (r < cnt) {
+                        const long long y = ld_label(p.labels, p.label_u8, base + (long long)r * p.W);
+                        if (y != p.ignore && y >= 0 && y < C) v = (unsigned)y;
+                    }
+                    labs |= (unsigned long long)v << (8 * r);
+                }
+            }
+        }
+
+        mbar_wait(&full[n % kFcStages], (uint32_t)((n / kFcStages) & 1));
+
+        if (cnt > 0) {
+            const int c0 = chunk * kFcNCH;
+            const int nvalid = min(kFcNCH, C - c0);
+            const LT* q00 = Sg + (i0 - ua) * G::BW + (j0 - jO);
+            const LT* q01 = Sg + (i0 - ua) * G::BW + (j1 - jO);
+            const LT* q10 = Sg + (i1 - ua) * G::BW + (j0 - jO);
+            const LT* q11 = Sg + (i1 - ua) * G::BW + (j1 - jO);
+            const float2 lw0_2 = splat(lw0), lw1_2 = splat(lw1);
+            float2 top[NP], bot[NP];
+            float nanflag = 0.f;
+            #pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                const float2 a = make_float2(Logit<LT>::ld(q00 + (2 * q) * G::PLANE), Logit<LT>::ld(q00 + (2 * q + 1) * G::PLANE));
+                const float2 c = make_float2(Logit<LT>::ld(q01 + (2 * q) * G::PLANE), Logit<LT>::ld(q01 + (2 * q + 1) * G::PLANE));
+                top[q] = lerp2_pinned(a, lw0_2, c, lw1_2);
+                const float2 d = make_float2(Logit<LT>::ld(q10 + (2 * q) * G::PLANE), Logit<LT>::ld(q10 + (2 * q + 1) * G::PLANE));
+                const float2 e = make_float2(Logit<LT>::ld(q11 + (2 * q) * G::PLANE), Logit<LT>::ld(q11 + (2 * q + 1) * G::PLANE));
+                bot[q] = lerp2_pinned(d, lw0_2, e, lw1_2);
+                if (2 * q < nvalid) nanflag = __fmaf_rn(top[q].x, 0.f, __fmaf_rn(bot[q].x, 0.f, nanflag));
+                if (2 * q + 1 < nvalid) nanflag = __fmaf_rn(top[q].y, 0.f, __fmaf_rn(bot[q].y, 0.f, nanflag));
+            }
+            const bool odd = nanflag != nanflag;                     // a NaN or Inf among this chunk's taps
+            #pragma unroll
+            for (int r = 0; r < S; ++r) {
+                if (r < cnt) {
+                    const float lh1 = u < 0 ? 0.0f : ((float)r + 0.5f) * (1.0f / S);
+                    const float lh0 = 1.0f - lh1;
+                    const float2 lh0_2 = splat(lh0), lh1_2 = splat(lh1);
+                    float2 z[NP];
+                    #pragma unroll
+                    for (int q = 0; q < NP; ++q) z[q] = rnd2<LT>(lerp2_pinned(top[q], lh0_2, bot[q], lh1_2));
+                    if (nvalid < kFcNCH) {                           // tail chunk: classes past C never win nor add
+                        #pragma unroll
+                        for (int q = 0; q < NP; ++q) {
+                            if (2 * q >= nvalid) z[q].x = -INFINITY;
+                            if (2 * q + 1 >= nvalid) z[q].y = -INFINITY;
+                        }
+                    }
+                    float cm = z[0].x;
+                    #pragma unroll
+                    for (int q = 0; q < NP; ++q) cm = fmaxf(cm, fmaxf(z[q].x, z[q].y));
+                    if (cm > m[r]) {                                 // the running max moved: find its first index here
+                        int ci = kFcNCH - 1;
+                        #pragma unroll
+                        for (int q = NP - 1; q >= 0; --q) {
+                            ci = (z[q].y == cm) ? 2 * q + 1 : ci;
+                            ci = (z[q].x == cm) ? 2 * q : ci;
+                        }
+                        if (SOFTMAX) s[r] *= ex2_approx(__fsub_rn(__fmul_rn(m[r], kLog2e), __fmul_rn(cm, kLog2e)));
+                        m[r] = cm; idx[r] = c0 + ci;
+                    }
+                    if (odd && !((nanlock >> r) & 1u)) {             // torch: NaN beats everything, first NaN wins
+                        int first = -1;
+                        #pragma unroll
+                        for (int q = NP - 1; q >= 0; --q) {
+                            if (z[q].y != z[q].y) first = 2 * q + 1;
+                            if (z[q].x != z[q].x) first = 2 * q;
+                        }
+                        if (first >= 0) { idx[r] = c0 + first; m[r] = INFINITY; s[r] = NAN; nanlock |= 1u << r; }
+                    }
+                    if (SOFTMAX) {
+                        if (m[r] > -INFINITY) {
+                            const float2 nm2 = splat(-__fmul_rn(m[r], kLog2e));
+                            float2 a2 = make_float2(0.f, 0.f), b2 = make_float2(0.f, 0.f);
+                            #pragma unroll
+                            for (int q = 0; q < NP; ++q) {
+                                const float2 e = __ffma2_rn(z[q], l2e2, nm2);
+                                const float2 ex = make_float2(ex2_approx(e.x), ex2_approx(e.y));
+                                if (q & 1) b2 = __fadd2_rn(b2, ex); else a2 = __fadd2_rn(a2, ex);
+                            }
+                            a2 = __fadd2_rn(a2, b2);
+                            s[r] += a2.x + a2.y;
+                        }
+                        const int yk = (int)((labs >> (8 * r)) & 0xffu) - c0;
+                        if (yk >= 0 && yk < nvalid) {                // label logit: same ops, same bits as its z[] entry
+                            const float t0 = lerp_pinned(Logit<LT>::ld(q00 + yk * G::PLANE), lw0, Logit<LT>::ld(q01 + yk * G::PLANE), lw1);
+                            const float t1 = lerp_pinned(Logit<LT>::ld(q10 + yk * G::PLANE), lw0, Logit<LT>::ld(q11 + yk * G::PLANE), lw1);
+                            zy[r] = Logit<LT>::rnd(lerp_pinned(t0, lh0, t1, lh1));
+                        }
+                    }
+                }
+            }
+        }
+
+        if (chunk == p.n_chunks - 1) {
+            // ---- tile epilogue: per-pixel outputs, histogram, loss sums ----
+            const long long px0 = ((long long)b * p.H + TP::first(min(u, p.h - 1))) * p.W + X;
+            float tile_loss = 0.f, tile_w = 0.f, tile_hard = 0.f;
+            const int rows = (u <= p.h - 1) ? TP::count(u, p.h) : 0;   // warp-uniform (a warp shares sy); cnt is 0 for idle columns
+            #pragma unroll
+            for (int r = 0; r < S; ++r) {
+                if (r < rows) {
+                    const int lab = (int)((labs >> (8 * r)) & 0xffu);
+                    const bool valid = cnt > 0 && lab != 255;
+                    if (SOFTMAX && cnt > 0) {
+                        const float m2 = __fmul_rn(m[r], kLog2e);
+                        const float corr = __fmaf_rn(m[r], kLog2e, -m2);
+                        const float lg = (log2f(s[r]) - corr) * kLn2;
+                        float l = 0.f;
+                        if (valid) {
+                            const float wy = cw_s[lab];
+                            l = wy * (lg - (zy[r] - m[r]));
+                            tile_loss += l; tile_w += wy; ++cnt_valid;
+                            if (l > p.thresh) { tile_hard += l; ++cnt_hard; }
+                        }
+                        const long long px = px0 + (long long)r * p.W;
+                        if (p.loss_px) p.loss_px[px] = l;
+                        if (p.lse_px) p.lse_px[px] = m[r] + lg;
+                    }
+                    if (want_hist) {
+                        const int key = valid ? lab * C + idx[r] : -1;
+                        const unsigned peers = __match_any_sync(0xffffffffu, key);
+                        if (key >= 0 && (peers & lane_lt) == 0) atomicAdd(&hist_s[key], __popc(peers));
+                    }
+                }
+            }
+            acc_loss += (double)tile_loss; acc_w += (double)tile_w; acc_hard += (double)tile_hard;
+        }
+
+        __syncthreads();                                             // all threads are done with this stage
+        if (tid == 0 && n + kFcStages < n_items) issue(n + kFcStages);
+    }
+
+    if (want_hist) {
+        for (int k = tid; k < C * C; k += kFcThreads) {
+            const int v = hist_s[k];
+            if (v) atomicAdd(p.hist + k, (unsigned long long)v);
+        }
+    }
+    if (SOFTMAX) {
+        const double r0d = block_sum<kFcThreads>(acc_loss, red_scratch);
+        const double r1d = block_sum<kFcThreads>(acc_w, red_scratch);
+        const double r2d = block_sum<kFcThreads>(acc_hard, red_scratch);
+        const double r3d = block_sum<kFcThreads>((double)cnt_valid, red_scratch);
+        const double r4d = block_sum<kFcThreads>((double)cnt_hard, red_scratch);
+        if (tid == 0) {
+            double* o = p.ws->partials[blockIdx.x];
+            o[0] = r0d; o[1] = r1d; o[2] = r2d; o[3] = r3d; o[4] = r4d;
+            if (blockIdx.x == 0) p.ws->n_partials = gridDim.x;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+template <typename LT, int S, bool SOFTMAX>
+static int fc_launch(const FwdArgs& a) {
+    using G = FcGeom<LT, S>;
+    if (a.w < G::BW || a.h < G::BH) return -1000;                   // the TMA box must fit inside the tensor
+    FcParams p{};
+    p.labels = a.labels; p.class_w = a.class_w; p.loss_px = a.loss_px; p.lse_px = a.lse_px; p.hist = a.hist;
+    p.ws = reinterpret_cast<Workspace*>(a.ws);
+    p.B = a.B; p.C = a.C; p.h = a.h; p.w = a.w; p.H = a.H; p.W = a.W; p.ignore = a.ignore; p.label_u8 = a.ydtype == SF_U8;
+    p.thresh = a.thresh;
+    p.tiles_x = (a.W + kFcTW - 1) / kFcTW;
+    p.tiles_y = (a.h + 1 + G::NGT - 1) / G::NGT;
+    p.n_chunks = (a.C + kFcNCH - 1) / kFcNCH;
+    const long long total = (long long)a.B * p.tiles_x * p.tiles_y;
+    if (total * p.n_chunks >= (1LL << 31)) return SF_ERR_SHAPE;
+    p.total_tiles = (int)total;
+    p.hist_bytes = a.hist ? round_up(a.C * a.C * 4, 16) : 16;
+    const size_t smem = (size_t)kFcStages * G::STAGE_BYTES + p.hist_bytes + kFcStages * 8 + 16;
+    if (smem > 227 * 1024) return SF_ERR_TOO_MANY_CLASSES;
+    CUtensorMap tmap{};
+    const int rc = make_logits_tmap(&tmap, a.logits, a.ldtype, a.B * a.C, a.h, a.w, kFcNCH, G::BH, G::BW);
+    if (rc != 0) return rc;
+    auto k = fwd_chunk_kernel<LT, S, SOFTMAX>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kFcThreads, smem);
+    if (per_sm < 1) per_sm = 1;
+    const int grid = (int)std::min<long long>(total, std::min(kMaxCtas, per_sm * sm_count()));
+    k<<<grid, kFcThreads, smem, reinterpret_cast<cudaStream_t>(a.stream)>>>(tmap, p);
+    return (int)cudaGetLastError();
+}
+
+template <typename LT, int S>
+static int fc_mode(const FwdArgs& a) {
+    return a.softmax ? fc_launch<LT, S, true>(a) : fc_launch<LT, S, false>(a);
+}
+template <typename LT>
+static int fc_scale(const FwdArgs& a, int s) {
+    switch (s) {
+        case 4: return fc_mode<LT, 4>(a);
+        case 8: return fc_mode<LT, 8>(a);
+        default: return -1000;
+    }
+}
+
+// Returns -1000 when the shape is not covered (the caller then takes the generic kernel).
+int launch_forward_chunk(const FwdArgs& a) {
+    if (a.force_no_tma || a.C <= 24 || a.C > 255 || a.h <= 0 || a.w <= 0 || a.H % a.h || a.W % a.w) return -1000;
+    const int s = a.H / a.h;
+    if (s != a.W / a.w) return -1000;
+    const int esz = a.ldtype == SF_F32 ? 4 : 2;
+    if (((size_t)a.w * esz) % 16 || ((uintptr_t)a.logits % 16)) return -1000;
+    if (a.ldtype == SF_F32) return fc_scale<float>(a, s);
+    if (a.ldtype == SF_BF16) return fc_scale<__nv_bfloat16>(a, s);
+    return fc_scale<__half>(a, s);
+}
+
+}  // namespace sf

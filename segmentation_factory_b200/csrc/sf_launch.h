@@ -23,6 +23,7 @@ struct FwdArgs {
 };
 int launch_forward(const FwdArgs& a);
 int launch_forward_fast(const FwdArgs& a);    // -1000: shape not covered by the integer-scale specialisation
+int launch_forward_chunk(const FwdArgs& a);   // integer scale, many classes (16-class chunks); -1000: not covered
 
 struct BwdArgs {
     const void* logits; int ldtype;
