@@ -19,7 +19,9 @@
 
 namespace sf {
 
-constexpr int kBfThreads = 256;
+constexpr int kBfThreads = 128;                // label columns per tile; small CTAs (4 per SM) decorrelate the phases of
+                                               // their row walks, which share the FMA / MUFU / ALU pipes
+constexpr int kBfJL = kBfThreads / 4;          // gather lanes along j (>= owned columns per tile)
 constexpr int kBfTH = 8;                       // owned low-res rows per tile
 constexpr int kBfBH = kBfTH + 2;               // staged source rows: ia-1 .. ia+TH
 
@@ -45,7 +47,7 @@ struct BfGeom {
     static constexpr int SRC_BYTES = round_up(C * PLANE * (int)sizeof(LT), 128);
     static constexpr int NP = C / 2;
     static constexpr bool ODD = (C & 1) != 0;
-    static constexpr int KQ = kBfThreads / 64;                      // channel phases of the gather (threads / 64)
+    static constexpr int KQ = kBfThreads / kBfJL;                   // channel phases of the gather
 };
 
 template <int C>
@@ -71,7 +73,7 @@ __device__ __forceinline__ void onehot_sub2(int y, float2 (&a0)[C / 2 > 0 ? C / 
 // ceil(Ctot / C) chunks, one CTA per (tile, chunk) -- chunks are independent in the backward because the softmax
 // denominator arrives as lse_px; label/lse/loss are re-read per chunk (L2 hits: the chunk index varies fastest).
 template <typename LT, int C, int S, bool CHUNK>
-__global__ void __launch_bounds__(kBfThreads, 2)
+__global__ void __launch_bounds__(kBfThreads, 4)
 bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
     static_assert(C <= 24, "onehot_sub2 covers 24 classes");
     using G = BfGeom<LT, C, S>;
@@ -100,7 +102,7 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
     const int ja = txi * G::TBW, jb = min(ja + G::TBW, p.w);
     const int nown = jb - ja;
     const int jO = (ja - 1) & ~(G::XAL - 1);                        // box x-origin: 16-byte aligned, -XAL for the first tile
-    if (tid < (CHUNK ? 256 : 32)) cw_s[tid] = (p.class_w && tid < Ct) ? __ldg(p.class_w + tid) : 1.0f;
+    for (int k = tid; k < (CHUNK ? 256 : 32); k += kBfThreads) cw_s[k] = (p.class_w && k < Ct) ? __ldg(p.class_w + k) : 1.0f;
     if (tid == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
@@ -118,7 +120,7 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
     const float2 lw0_2 = splat(lw0), lw1_2 = splat(lw1);
 
     // ---- gather role: owned column jl = tid % 64, channels kq, kq+KQ, ...; 2S constant weights ----
-    const int jl = tid & 63, kq = tid >> 6;
+    const int jl = tid % kBfJL, kq = tid / kBfJL;
     const bool gat = jl < nown;
     float wgt[2 * S];
     {
