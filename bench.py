@@ -265,7 +265,7 @@ def main():
     tp = os.path.join(ROOT, "profiles", "traffic_latest.json")     # dram read+write bytes per launch from ncu --set full
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get(dom)
-    roofline = {"bound": "hbm", "kernel": f"sf::{dom}_kernel<float,19>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": f"sf::{dom}_fast_kernel<float,19,4>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "kernel_ms": kern, "step_frac": algorithmic_bytes_per_px("step") * n_px / (ms_step * 1e-3) / 1e9 / peak,
                 "note": "at C=19 and 1/16 logit density the path is issue/MUFU-bound, not HBM-bound (DESIGN.md)"}
