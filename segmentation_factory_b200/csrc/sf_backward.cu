@@ -272,7 +272,9 @@ int launch_backward(const BwdArgs& a) {
         (a.ydtype == SF_I64 && ((uintptr_t)a.labels % 8))) return SF_ERR_ALIGN;
 
     if (!env_no_fast()) {
-        const int rc = launch_backward_fast(a);                    // integer-scale specialisation (sf_backward_fast.cu)
+        int rc = launch_backward_direct(a);                        // logits already at label resolution (sf_direct.cu)
+        if (rc != -1000) return rc;
+        rc = launch_backward_fast(a);                              // integer-scale specialisation (sf_backward_fast.cu)
         if (rc != -1000) return rc;
     }
     BwdParams p{};

@@ -339,7 +339,9 @@ int launch_forward(const FwdArgs& a) {
     if (((uintptr_t)a.logits % esz) || (a.ydtype == SF_I64 && ((uintptr_t)a.labels % 8))) return SF_ERR_ALIGN;
     if ((long long)a.B * a.H * a.W >= (1LL << 40) || (long long)a.B * a.C >= (1LL << 31)) return SF_ERR_SHAPE;
     if (!env_no_fast()) {
-        int rc = launch_forward_fast(a);                           // integer-scale specialisation (sf_forward_fast.cu)
+        int rc = launch_forward_direct(a);                         // logits already at label resolution (sf_direct.cu)
+        if (rc != -1000) return rc;
+        rc = launch_forward_fast(a);                               // integer-scale specialisation (sf_forward_fast.cu)
         if (rc != -1000) return rc;
         rc = launch_forward_chunk(a);                              // integer scale, > 24 classes (sf_forward_chunk.cu)
         if (rc != -1000) return rc;

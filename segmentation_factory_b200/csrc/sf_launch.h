@@ -23,6 +23,7 @@ struct FwdArgs {
 };
 int launch_forward(const FwdArgs& a);
 int launch_forward_fast(const FwdArgs& a);    // -1000: shape not covered by the integer-scale specialisation
+int launch_forward_direct(const FwdArgs& a);  // h == H, w == W: streaming kernels, no interpolation; -1000: not covered
 int launch_forward_chunk(const FwdArgs& a);   // integer scale, many classes (16-class chunks); -1000: not covered
 
 struct BwdArgs {
@@ -38,6 +39,7 @@ struct BwdArgs {
     bool force_no_tma;
 };
 int launch_backward(const BwdArgs& a);
+int launch_backward_direct(const BwdArgs& a);
 int launch_backward_fast(const BwdArgs& a);   // -1000: shape not covered
 
 int launch_finalize(const float* loss_px, long long n_px, float thresh, void* ws, float* loss_out, void* stream);

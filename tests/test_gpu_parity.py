@@ -132,6 +132,8 @@ CASES = [
     ("nonint_up", 80, 2, 19, 100, 130, 333, 517, "late", torch.float32, torch.int64, "ohem", False),
     ("downscale", 81, 1, 7, 300, 260, 200, 180, "early", torch.float32, torch.int64, "ce", False),
     ("fullres_identity", 82, 1, 19, 256, 320, 256, 320, "early", torch.float32, torch.int64, "ohem", False),
+    ("fullres_bf16_c150", 83, 2, 150, 128, 160, 128, 160, "early", torch.bfloat16, torch.uint8, "ce", True),
+    ("fullres_fp16_late", 84, 2, 21, 192, 256, 192, 256, "late", torch.float16, torch.int64, "ohem", False),
 ]
 
 
@@ -244,6 +246,27 @@ def test_nan_and_inf_logits_follow_torch_argmax(sf):
     ref = tr.confusion_counts(tr.upsample(low, (128, 256)), lab, 19)
     assert torch.equal(hist.cpu(), ref)
     assert torch.isnan(sf.CrossEntropy()(low.cuda(), lab.cuda())).item()
+
+
+def test_same_size_nan_argmax_and_error_codes(sf):
+    """Full-resolution logits (the unmodified engine.py call): first-NaN argmax like torch; C*C histogram too large for
+    shared memory is reported, not silently mis-counted."""
+    from oracle import torch_restatement as tr
+    from segmentation_factory_b200._lib import SegFactoryError
+    low, lab = _synth(11, 1, 19, 128, 256, 128, 256, "early")
+    low[0, 7, 5, 9] = float("nan")
+    low[0, 3, 5, 9] = float("nan")
+    low[0, 2, 60, 60] = float("inf")
+    hist = torch.zeros(19, 19, dtype=torch.int64, device="cuda")
+    sf.eval_hist(low.cuda(), lab.cuda(), 255, hist)
+    assert torch.equal(hist.cpu(), tr.confusion_counts(low, lab, 19))
+    big = torch.randn(1, 300, 32, 64, device="cuda")
+    lab2 = torch.zeros(1, 128, 256, dtype=torch.long, device="cuda")
+    with pytest.raises(SegFactoryError):
+        sf.eval_hist(big, lab2, 255, torch.zeros(300, 300, dtype=torch.int64, device="cuda"))
+    loss = sf.CrossEntropy()(big, lab2)                              # loss only (no matrix): any C works
+    ref = torch.nn.functional.cross_entropy(torch.nn.functional.interpolate(big, size=(128, 256), mode="bilinear", align_corners=False), lab2)
+    assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
 
 
 def test_c_abi_direct_call(sf):
