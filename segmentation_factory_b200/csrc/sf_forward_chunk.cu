@@ -143,7 +143,6 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmap, const FcParams p) {
             const LT* q11 = Sg + (i1 - ua) * G::BW + (j1 - jO);
             const float2 lw0_2 = splat(lw0), lw1_2 = splat(lw1);
             float2 top[NP], bot[NP];
-            float nanflag = 0.f;
             #pragma unroll
             for (int q = 0; q < NP; ++q) {
                 const float2 a = make_float2(Logit<LT>::ld(q00 + (2 * q) * G::PLANE), Logit<LT>::ld(q00 + (2 * q + 1) * G::PLANE));
@@ -152,9 +151,14 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmap, const FcParams p) {
                 const float2 d = make_float2(Logit<LT>::ld(q10 + (2 * q) * G::PLANE), Logit<LT>::ld(q10 + (2 * q + 1) * G::PLANE));
                 const float2 e = make_float2(Logit<LT>::ld(q11 + (2 * q) * G::PLANE), Logit<LT>::ld(q11 + (2 * q + 1) * G::PLANE));
                 bot[q] = lerp2_pinned(d, lw0_2, e, lw1_2);
-                if (2 * q < nvalid) nanflag = __fmaf_rn(top[q].x, 0.f, __fmaf_rn(bot[q].x, 0.f, nanflag));
-                if (2 * q + 1 < nvalid) nanflag = __fmaf_rn(top[q].y, 0.f, __fmaf_rn(bot[q].y, 0.f, nanflag));
             }
+            // NaN / Inf probe over the chunk's taps: x * 0 is NaN exactly for NaN and Inf.  Packed, no per-class predicate:
+            // the classes past C of a tail chunk hold finite neighbours' data or TMA zero fill.
+            float2 nan2 = make_float2(0.f, 0.f);
+            const float2 zero2 = make_float2(0.f, 0.f);
+            #pragma unroll
+            for (int q = 0; q < NP; ++q) nan2 = __ffma2_rn(top[q], zero2, __ffma2_rn(bot[q], zero2, nan2));
+            const float nanflag = nan2.x + nan2.y;
             const bool odd = nanflag != nanflag;                     // a NaN or Inf among this chunk's taps
             #pragma unroll
             for (int r = 0; r < S; ++r) {
