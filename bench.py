@@ -181,7 +181,20 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL printf()s its version banner to stdout at communicator creation; stdout must carry ONE JSON line, so fd 1 is
+        # pointed at stderr while the communicator is created and the first collective runs.
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize(dev)
+        finally:
+            ctypes.CDLL(None).fflush(None)
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     L = _lib.lib()
     thr = float(-torch.log(torch.tensor(0.7, dtype=torch.float)))
@@ -211,15 +224,19 @@ def main():
         rc |= L.sf_loss_finalize(loss_px.data_ptr(), n_px, ctypes.c_float(thr), ws.data_ptr(), ws_bytes, out.data_ptr(), st)
         if evs:
             evs[2].record(stream)
+        work = None
+        if world > 1:
+            # the path's one exchange: int64 matrix (+ counters) SUM over NVLink.  The matrix is final after the forward,
+            # so the collective is issued here and runs on NCCL's stream underneath the backward kernel.
+            work = dist.all_reduce(hist, async_op=True)
         rc |= L.sf_ce_backward(lo.data_ptr(), 0, la.data_ptr(), 0, B, C, LH, LW, H, W, 255, None, loss_px.data_ptr(),
                                lse_px.data_ptr(), None, ws.data_ptr(), grad.data_ptr(), st)
         if evs:
             evs[3].record(stream)
         if rc:
             raise RuntimeError(f"kernel launch failed rc={rc}")
-        if world > 1:
-            # the path's one exchange: int64 matrix (+ counters) SUM over NVLink, overlapped with nothing else here
-            dist.all_reduce(hist)
+        if work is not None:
+            work.wait()                                      # stream-level wait, no host sync
 
     def barrier():
         if world > 1:
@@ -339,7 +356,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "logits": args.kind, "ohem_branch": int(state[4]), "labels": "int64, 10% ignore=255",
                        "l2": f"inputs rotate over {N_SETS} distinct batches ({N_SETS * h2d / 1e6:.0f} MB > 126 MB L2)",
-                       "parallelism": f"dp{world}", "collective": "all_reduce(int64[C*C+2]) per step" if world > 1 else "none"},
+                       "parallelism": f"dp{world}", "collective": "all_reduce(int64[C*C+2]) per step, overlapped with the backward" if world > 1 else "none"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": 3 * args.steps, "roofline": roofline, "cpu_baseline": cpu,
         }))
     if world > 1:
