@@ -46,13 +46,15 @@ typedef struct sf_loss_state {
     float    kth;         /* pixels with loss_px >  kth are kept with weight 1                  */
     float    tie_share;   /* pixels with loss_px == kth are kept with this weight (top-k ties)  */
     float    inv_denom;   /* 1/K (OHEM) or 1/sum(w_y) (CE): d loss / d loss_px of a kept pixel  */
-    int32_t  branch;      /* 0 = CE, 1 = OHEM threshold branch, 2 = OHEM top-k branch           */
+    int32_t  branch;      /* 0 = CE, 1 = OHEM threshold branch, 2 = OHEM top-k branch, 3 = focal */
     int32_t  reserved;
     uint64_t n_valid;     /* non-ignored pixels                                                 */
     uint64_t n_hard;      /* pixels with loss_px > thresh                                       */
     uint64_t n_kept;      /* K                                                                  */
     double   sum_kept;    /* sum of kept per-pixel losses                                       */
     double   sum_w;       /* sum of class weights over valid pixels                             */
+    float    focal_alpha; /* branch 3: FocalLoss alpha ...                                      */
+    float    focal_gamma; /* ... and gamma; d loss / d ce_px = a[(1-pt)^g + g ce pt (1-pt)^(g-1)] */
 } sf_loss_state;
 
 int         sf_version(void);
@@ -95,6 +97,14 @@ int sf_ce_forward(const void* logits, int ldtype, const void* labels, int ydtype
  */
 int sf_loss_finalize(const float* loss_px, long long n_px, float ohem_thresh,
                      void* workspace, size_t workspace_bytes, float* loss_out, void* stream);
+
+/*
+ * Replaces util/losses.py:9-25 (FocalLoss: alpha * (1 - exp(-ce))**gamma * ce, mean over ALL pixels or sum) on the
+ * per-pixel cross-entropy sf_ce_forward wrote to loss_px (call it with ohem_thresh < 0 and class_w = NULL).
+ * Writes sf_loss_state (branch 3) so that sf_ce_backward applies d focal / d ce per pixel.
+ */
+int sf_focal_finalize(const float* loss_px, long long n_px, float alpha, float gamma, int size_average,
+                      void* workspace, size_t workspace_bytes, float* loss_out, void* stream);
 
 /*
  * Replaces autograd's nll_loss2d_backward + _log_softmax_backward_data + upsample_bilinear2d_backward.

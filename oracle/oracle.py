@@ -182,3 +182,23 @@ def ohem_loss_and_grad(logits, labels, ignore=255, class_w=None, thresh=OHEM_THR
             coef = coef.astype(np.float32)
         grad = path_backward(logits, labels, f["lse_px"], coef, ignore, class_w, ldtype)
     return loss, grad, dict(kth=kth, kept=kept, branch=branch, n_valid=int(f["sums"][2]), n_hard=int(f["sums"][3]))
+
+
+def focal_loss_and_grad(logits, labels, alpha=1.0, gamma=0.0, size_average=True, ignore=255, ldtype=None, want_grad=True):
+    """FocalLoss (util/losses.py:9-25): alpha * (1 - exp(-ce))**gamma * ce, mean over ALL pixels (ignored ones are
+    zeros) or sum.  ce is the unweighted per-pixel cross-entropy; the gradient flows through ce only."""
+    f = path_forward(logits, labels, ignore, None, 0.0, ldtype, want_arg=False, want_hist=False)
+    ce = f["loss_px"].astype(np.float64)
+    pt = np.exp(-ce)
+    om = 1.0 - pt
+    with np.errstate(divide="ignore", invalid="ignore"):
+        w = np.where(om > 0, om ** gamma, 1.0 if gamma == 0 else 0.0)
+        dw = np.where(om > 0, gamma * om ** (gamma - 1.0) * pt, 0.0)         # d (1-pt)^g / d ce
+    val = alpha * w * ce
+    denom = ce.size if size_average else 1.0
+    loss = float(val.sum() / denom)
+    grad = None
+    if want_grad:
+        coef = (alpha * (w + ce * dw) / denom).astype(np.float32)
+        grad = path_backward(logits, labels, f["lse_px"], coef, ignore, None, ldtype)
+    return loss, grad

@@ -6,10 +6,10 @@ Mirrors the reference's util/ API for this path only:
     ConfusionMatrix                                 (util/utils.py)
 backed by hand-written sm_100a kernels in libsegfactory.so (C ABI: include/segfactory.h).
 """
-from .losses import CrossEntropy, OhemCrossEntropy, get_loss
+from .losses import CrossEntropy, FocalLoss, OhemCrossEntropy, get_loss
 from .metrics import ConfusionMatrix, Metrics, fused_eval_update
-from .functional import eval_hist, fused_cross_entropy, hist_pairs
+from .functional import eval_hist, fused_cross_entropy, fused_focal_loss, hist_pairs
 
-__all__ = ["CrossEntropy", "OhemCrossEntropy", "get_loss", "Metrics", "ConfusionMatrix",
+__all__ = ["CrossEntropy", "OhemCrossEntropy", "FocalLoss", "fused_focal_loss", "get_loss", "Metrics", "ConfusionMatrix",
            "fused_eval_update", "fused_cross_entropy", "eval_hist", "hist_pairs"]
 __version__ = "0.1.0"

@@ -110,6 +110,13 @@ int sf_loss_finalize(const float* loss_px, long long n_px, float ohem_thresh, vo
     return sf::launch_finalize(loss_px, n_px, ohem_thresh, workspace, loss_out, stream);
 }
 
+int sf_focal_finalize(const float* loss_px, long long n_px, float alpha, float gamma, int size_average, void* workspace,
+                      size_t workspace_bytes, float* loss_out, void* stream) {
+    if (!workspace || !loss_px || n_px <= 0) return SF_ERR_ARG;
+    if (workspace_bytes < sizeof(sf::Workspace)) return SF_ERR_WORKSPACE;
+    return sf::launch_focal(loss_px, n_px, alpha, gamma, size_average, workspace, loss_out, stream);
+}
+
 int sf_ce_backward(const void* logits, int ldtype, const void* labels, int ydtype, int B, int C, int h, int w, int H,
                    int W, int ignore, const float* class_w, const float* loss_px, const float* lse_px,
                    const float* grad_out, const void* workspace, void* grad_logits, void* stream) {

@@ -175,6 +175,17 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+// FocalLoss (util/losses.py:17-25): f = a (1-pt)^g ce with pt = exp(-ce).  Returns f; *dfdce = a[(1-pt)^g + g ce pt (1-pt)^(g-1)].
+__device__ __forceinline__ float focal_value(float ce, float alpha, float gamma, float* dfdce) {
+    const float pt = expf(-ce);
+    const float om = 1.0f - pt;
+    if (gamma == 0.0f) { *dfdce = alpha; return alpha * ce; }
+    if (!(om > 0.0f)) { *dfdce = 0.0f; return 0.0f; }               // ce == 0 (also every ignored pixel)
+    const float w = powf(om, gamma);
+    *dfdce = alpha * (w + gamma * ce * pt * (w / om));
+    return alpha * w * ce;
+}
+
 __device__ __forceinline__ long long ld_label(const void* labels, int is_u8, long long idx) {
     return is_u8 ? (long long)__ldg(reinterpret_cast<const unsigned char*>(labels) + idx)
                  : __ldg(reinterpret_cast<const long long*>(labels) + idx);

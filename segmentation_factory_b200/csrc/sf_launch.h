@@ -43,6 +43,8 @@ int launch_backward_direct(const BwdArgs& a);
 int launch_backward_fast(const BwdArgs& a);   // -1000: shape not covered
 
 int launch_finalize(const float* loss_px, long long n_px, float thresh, void* ws, float* loss_out, void* stream);
+int launch_focal(const float* loss_px, long long n_px, float alpha, float gamma, int size_average, void* ws,
+                 float* loss_out, void* stream);
 int launch_hist_pairs(const void* a, int adtype, const long long* b, long long n, int C,
                       unsigned long long* mat, void* stream);
 

@@ -110,7 +110,7 @@ finalize_kernel(const float* __restrict__ loss_px, long long n, float thresh, Wo
     const unsigned long long n_valid = (unsigned long long)tot[3], n_hard = (unsigned long long)tot[4];
     const bool writer = blockIdx.x == 0 && threadIdx.x == 0;
     sf_loss_state st;
-    st.reserved = 0; st.n_valid = n_valid; st.n_hard = n_hard; st.sum_w = sum_w; st.tie_share = 0.f;
+    st.reserved = 0; st.focal_alpha = 0.f; st.focal_gamma = 0.f; st.n_valid = n_valid; st.n_hard = n_hard; st.sum_w = sum_w; st.tie_share = 0.f;
 
     if (thresh < 0.f) {                                             // CrossEntropy: sum(w_y l) / sum(w_y)
         if (writer) {
@@ -179,6 +179,54 @@ finalize_kernel(const float* __restrict__ loss_px, long long n, float thresh, Wo
             if (loss_out) *loss_out = st.loss;
         }
     }
+}
+
+// FocalLoss reduction (util/losses.py:17-25) over the per-pixel CE: one persistent pass, per-CTA partials in a fixed
+// order, the last CTA to finish (atomic ticket) sums them and writes the state -- deterministic, single launch.
+__global__ void __launch_bounds__(kSelThreads)
+focal_kernel(const float* __restrict__ ce, long long n, float alpha, float gamma, int size_average, Workspace* ws,
+             float* loss_out) {
+    __shared__ double red[kSelThreads / 32];
+    __shared__ bool last;
+    double a = 0.0;
+    const long long stride = (long long)gridDim.x * kSelThreads;
+    for (long long i = (long long)blockIdx.x * kSelThreads + threadIdx.x; i < n; i += stride) {
+        float d;
+        a += (double)focal_value(__ldg(ce + i), alpha, gamma, &d);
+    }
+    const double cta = block_sum<kSelThreads>(a, red);
+    if (threadIdx.x == 0) {
+        ws->sel_partials[blockIdx.x] = cta;
+        __threadfence();
+        last = atomicAdd(&ws->radix_hist[0][0], 1u) == gridDim.x - 1;   // ticket counter, reset below
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    double b = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += kSelThreads) b += __ldcg(&ws->sel_partials[i]);
+    const double tot = block_sum<kSelThreads>(b, red);
+    if (threadIdx.x == 0) {
+        ws->radix_hist[0][0] = 0;
+        sf_loss_state st;
+        st.reserved = 0; st.n_valid = 0; st.n_hard = 0; st.n_kept = (unsigned long long)n; st.sum_w = 0.0;
+        const double denom = size_average ? (double)n : 1.0;
+        st.loss = (float)(tot / denom); st.kth = 0.f; st.tie_share = 0.f; st.inv_denom = (float)(1.0 / denom);
+        st.branch = 3; st.focal_alpha = alpha; st.focal_gamma = gamma; st.sum_kept = tot;
+        ws->state = st;
+        if (loss_out) *loss_out = st.loss;
+    }
+}
+
+int launch_focal(const float* loss_px, long long n_px, float alpha, float gamma, int size_average, void* ws,
+                 float* loss_out, void* stream) {
+    Workspace* w = reinterpret_cast<Workspace*>(ws);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(&w->radix_hist[0][0], 0, sizeof(unsigned), st);   // ticket counter
+    if (e != cudaSuccess) return (int)e;
+    const int grid = (int)std::min<long long>((n_px + kSelThreads - 1) / kSelThreads, std::min(2 * sm_count(), kMaxCtas));
+    focal_kernel<<<grid, kSelThreads, 0, st>>>(loss_px, n_px, alpha, gamma, size_average, w, loss_out);
+    return (int)cudaGetLastError();
 }
 
 int launch_finalize(const float* loss_px, long long n_px, float thresh, void* ws, float* loss_out, void* stream) {

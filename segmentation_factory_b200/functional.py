@@ -96,7 +96,7 @@ class _FusedCE(torch.autograd.Function):
     """upsample + (OHEM) cross-entropy; forward = sf_ce_forward + sf_loss_finalize, backward = sf_ce_backward."""
 
     @staticmethod
-    def forward(ctx, logits, labels, class_w, ignore, thresh, hist):
+    def forward(ctx, logits, labels, class_w, ignore, thresh, hist, focal=None):
         L = _lib.lib()
         B, C, h, w = logits.shape
         _, H, W = labels.shape
@@ -104,9 +104,10 @@ class _FusedCE(torch.autograd.Function):
         n_px = B * H * W
         ohem = thresh >= 0.0
         need_grad = ctx.needs_input_grad[0]
+        keep_loss = ohem or focal is not None            # focal: the per-pixel CE is what the epilogue transforms
         ws_bytes = L.sf_workspace_bytes()
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        loss_px = torch.empty(n_px, dtype=torch.float32, device=dev) if ohem else None
+        loss_px = torch.empty(n_px, dtype=torch.float32, device=dev) if keep_loss else None
         lse_px = torch.empty(n_px, dtype=torch.float32, device=dev) if need_grad else None
         out = torch.empty((), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
@@ -115,8 +116,14 @@ class _FusedCE(torch.autograd.Function):
                                  B, C, h, w, H, W, int(ignore), _ptr(class_w), float(thresh),
                                  _ptr(loss_px), _ptr(lse_px), _ptr(hist), _ptr(ws), ws_bytes, st)
             _lib.check(rc, "sf_ce_forward")
-            rc = L.sf_loss_finalize(_ptr(loss_px), n_px, float(thresh), _ptr(ws), ws_bytes, _ptr(out), st)
-            _lib.check(rc, "sf_loss_finalize")
+            if focal is None:
+                rc = L.sf_loss_finalize(_ptr(loss_px), n_px, float(thresh), _ptr(ws), ws_bytes, _ptr(out), st)
+                _lib.check(rc, "sf_loss_finalize")
+            else:
+                alpha, gamma, size_average = focal
+                rc = L.sf_focal_finalize(_ptr(loss_px), n_px, float(alpha), float(gamma), int(bool(size_average)),
+                                         _ptr(ws), ws_bytes, _ptr(out), st)
+                _lib.check(rc, "sf_focal_finalize")
         ctx.ignore = int(ignore)
         ctx.ws = ws                      # plain attribute: the workspace is an opaque device scratch
         ctx.save_for_backward(logits, labels, class_w, loss_px, lse_px)
@@ -136,7 +143,7 @@ class _FusedCE(torch.autograd.Function):
                                   B, C, h, w, H, W, ctx.ignore, _ptr(class_w), _ptr(loss_px), _ptr(lse_px),
                                   _ptr(g), _ptr(ctx.ws), _ptr(grad), _stream(dev))
         _lib.check(rc, "sf_ce_backward")
-        return grad, None, None, None, None, None
+        return grad, None, None, None, None, None, None
 
 
 def fused_cross_entropy(logits, labels, weight=None, ignore_index=255, ohem_thresh=None, hist=None):
@@ -152,4 +159,13 @@ def fused_cross_entropy(logits, labels, weight=None, ignore_index=255, ohem_thre
         raise ValueError("ohem_thresh must be a finite non-negative loss value")
     if hist is not None and (hist.dtype != torch.int64 or hist.numel() != C * C or not hist.is_contiguous()):
         raise ValueError("hist must be a contiguous int64 [C, C] tensor")
-    return _FusedCE.apply(logits, labels, cw, int(ignore_index), thresh, hist)
+    return _FusedCE.apply(logits, labels, cw, int(ignore_index), thresh, hist, None)
+
+
+def fused_focal_loss(logits, labels, alpha=1.0, gamma=0.0, size_average=True, ignore_index=255):
+    """FocalLoss of util/losses.py:9-25 on logits that may be lower-resolution than the labels:
+    alpha * (1 - exp(-ce))**gamma * ce per pixel (ce = 0 where ignored), mean over ALL pixels or sum."""
+    logits = prep_logits(logits)
+    B, C, h, w = logits.shape
+    labels = prep_labels(labels, B, (h, w))
+    return _FusedCE.apply(logits, labels, None, int(ignore_index), -1.0, None, (float(alpha), float(gamma), bool(size_average)))

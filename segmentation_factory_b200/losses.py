@@ -10,9 +10,9 @@ from __future__ import annotations
 import torch
 from torch import Tensor, nn
 
-from .functional import fused_cross_entropy
+from .functional import fused_cross_entropy, fused_focal_loss
 
-__all__ = ["CrossEntropy", "OhemCrossEntropy", "get_loss"]
+__all__ = ["CrossEntropy", "OhemCrossEntropy", "FocalLoss", "get_loss"]
 
 
 class CrossEntropy(nn.Module):
@@ -54,8 +54,24 @@ class OhemCrossEntropy(nn.Module):
         return self._forward(preds, labels)
 
 
+class FocalLoss(nn.Module):
+    """util/losses.py:9-25: an epilogue on the per-pixel cross-entropy.
+    Same constructor; the mean runs over all pixels, ignored ones included as zeros, like the reference."""
+
+    def __init__(self, alpha=1, gamma=0, size_average=True, ignore_index=255):
+        super().__init__()
+        self.alpha = alpha
+        self.gamma = gamma
+        self.ignore_index = ignore_index
+        self.size_average = size_average
+
+    def forward(self, inputs, targets):
+        return fused_focal_loss(inputs, targets, self.alpha, self.gamma, self.size_average, self.ignore_index)
+
+
 def get_loss(loss_fn_name: str = "CrossEntropy", ignore_label: int = 255, cls_weights: Tensor = None):
-    """util/losses.py:118-122.  Dice / FocalLoss are outside this path."""
-    table = {"CrossEntropy": CrossEntropy, "OhemCrossEntropy": OhemCrossEntropy}
+    """util/losses.py:118-122.  Dice is outside this path; the reference's own get_loss would
+    call FocalLoss(ignore_label, cls_weights) positionally, i.e. as (alpha, gamma) -- kept as is."""
+    table = {"CrossEntropy": CrossEntropy, "OhemCrossEntropy": OhemCrossEntropy, "FocalLoss": FocalLoss}
     assert loss_fn_name in table, f"Unavailable loss function name >> {loss_fn_name}.\nAvailable loss functions: {list(table)}"
     return table[loss_fn_name](ignore_label, cls_weights)

@@ -18,7 +18,19 @@ def pytest_configure(config):
 
 def golden_names():
     return sorted(os.path.splitext(os.path.basename(p))[0]
-                  for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if "hist_f32" not in p)
+                  for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
+                  if "hist_f32" not in p and not os.path.basename(p).startswith("focal_"))
+
+
+def focal_names():
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "focal_*.npz")))
+
+
+def load_focal(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+    d = {k: z[k] for k in z.files}
+    d["logits_dtype"] = str(d["logits_dtype"])
+    return d
 
 
 def load_golden(name):

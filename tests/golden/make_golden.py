@@ -21,7 +21,7 @@ import torch.nn.functional as F
 REF = os.environ.get("SEGFACTORY_REFERENCE", "/root/reference")
 sys.dont_write_bytecode = True
 sys.path.insert(0, REF)
-from util.losses import CrossEntropy, OhemCrossEntropy  # noqa: E402
+from util.losses import CrossEntropy, FocalLoss, OhemCrossEntropy  # noqa: E402
 from util.metrics import Metrics  # noqa: E402
 from util.utils import ConfusionMatrix  # noqa: E402
 
@@ -114,6 +114,22 @@ def run_case(name, seed, B, C, hw, HW, kind, dtype=torch.float32, ldt=torch.int6
           f"miou={iou[1]} up={d['up_sha256'][:12]}")
 
 
+def focal_case(name, seed, B, C, hw, HW, kind, alpha, gamma, size_average, dtype=torch.float32):
+    """FocalLoss (util/losses.py:9-25) through the upsample, value and gradient."""
+    g = torch.Generator().manual_seed(seed)
+    (h, w), (H, W) = hw, HW
+    labels = make_labels(g, B, C, H, W)
+    low = make_logits(g, kind, B, C, h, w, labels).to(dtype)
+    lowg = low.clone().requires_grad_(True)
+    up = F.interpolate(lowg, size=(H, W), mode="bilinear", align_corners=False).float()
+    val = FocalLoss(alpha, gamma, size_average, 255)(up, labels)
+    val.backward()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), logits=bits(low), logits_dtype=str(dtype).replace("torch.", ""),
+                        labels=labels.numpy(), size=np.array([H, W]), alpha=np.float32(alpha), gamma=np.float32(gamma),
+                        size_average=np.int32(size_average), loss=np.float32(val.item()), grad=lowg.grad.float().numpy())
+    print(f"{name:28s} focal={val.item():.6f}")
+
+
 def hist_f32_case():
     """Metrics.hist float32 accumulation past 2**24 and compute_* on a big matrix."""
     g = torch.Generator().manual_seed(99)
@@ -160,3 +176,6 @@ if __name__ == "__main__":
     run_case("all_ignored_ohem", 41, 1, 19, (16, 32), (64, 128), "early", all_ignored=True)
     run_case("all_ignored_ce", 42, 1, 19, (16, 32), (64, 128), "early", loss="ce", all_ignored=True)
     hist_f32_case()
+    focal_case("focal_g2_mean", 51, 2, 19, (16, 32), (64, 128), "early", 0.25, 2.0, True)
+    focal_case("focal_default", 52, 1, 19, (16, 32), (64, 128), "late", 1, 0, True)
+    focal_case("focal_g15_sum_bf16", 53, 1, 21, (30, 41), (100, 135), "early", 0.5, 1.5, False, torch.bfloat16)

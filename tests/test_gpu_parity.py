@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import golden_names, load_golden
+from conftest import focal_names, golden_names, load_focal, load_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -267,6 +267,34 @@ def test_same_size_nan_argmax_and_error_codes(sf):
     loss = sf.CrossEntropy()(big, lab2)                              # loss only (no matrix): any C works
     ref = torch.nn.functional.cross_entropy(torch.nn.functional.interpolate(big, size=(128, 256), mode="bilinear", align_corners=False), lab2)
     assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+
+
+@pytest.mark.parametrize("name", focal_names())
+def test_focal_loss_golden(sf, name):
+    g = load_focal(name)
+    if g["logits_dtype"] == "float32":
+        low = torch.from_numpy(g["logits"])
+    else:
+        low = torch.from_numpy(g["logits"].view(np.int16)).view(TDT[g["logits_dtype"]])
+    x = low.cuda().requires_grad_(True)
+    crit = sf.FocalLoss(float(g["alpha"]), float(g["gamma"]), bool(g["size_average"]), 255)
+    loss = crit(x, torch.from_numpy(g["labels"]).cuda())
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    loss.backward()
+    tol = 1e-5 if g["logits_dtype"] == "float32" else 2e-2
+    assert np.abs(x.grad.float().cpu().numpy() - g["grad"]).max() <= tol * np.abs(g["grad"]).max()
+
+
+def test_focal_loss_fast_paths_vs_oracle(sf, oracle):
+    """FocalLoss on the Cityscapes-shaped fast kernels and on same-size logits."""
+    for (B, C, h, w, H, W) in [(1, 19, 128, 256, 512, 1024), (1, 19, 128, 256, 128, 256)]:
+        low, lab = _synth(91, B, C, h, w, H, W, "early")
+        x = low.cuda().requires_grad_(True)
+        loss = sf.FocalLoss(0.25, 2.0)(x, lab.cuda())
+        loss.backward()
+        ref, grad = oracle.focal_loss_and_grad(low.numpy(), lab.numpy(), 0.25, 2.0, True)
+        assert abs(loss.item() - ref) <= 1e-5 * abs(ref)
+        assert np.abs(x.grad.cpu().numpy() - grad).max() <= 1e-5 * np.abs(grad).max()
 
 
 def test_c_abi_direct_call(sf):

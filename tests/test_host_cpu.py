@@ -15,7 +15,7 @@ from conftest import GOLDEN_DIR, ROOT, golden_names, load_golden
 def test_library_exports_every_declared_symbol():
     from segmentation_factory_b200 import _lib
     header = open(os.path.join(ROOT, "include", "segfactory.h")).read()
-    declared = set(re.findall(r"\b(sf_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"^(?:int|size_t|const char\*)\s+(sf_[a-z_]+)\s*\(", header, flags=re.M))
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     L = _lib.lib()
     for name in declared:
@@ -39,6 +39,8 @@ def test_no_cpu_fallback_and_input_validation():
         sf.ConfusionMatrix(19).update(y.flatten(), y.flatten())
     with pytest.raises(AssertionError):
         sf.get_loss("Dice")
+    with pytest.raises(SegFactoryError):
+        sf.FocalLoss(0.25, 2.0)(x, y)
     assert isinstance(sf.get_loss("CrossEntropy", 255, None), sf.CrossEntropy)
     o = sf.OhemCrossEntropy(thresh=0.7)
     assert o.thresh.dtype == torch.float32 and abs(float(o.thresh) - 0.35667494) < 1e-7   # util/losses.py:49

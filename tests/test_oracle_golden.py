@@ -5,7 +5,7 @@ import hashlib
 import numpy as np
 import pytest
 
-from conftest import golden_names, load_golden
+from conftest import focal_names, golden_names, load_focal, load_golden
 
 DT = {"float32": 0, "bfloat16": 1, "float16": 2}
 
@@ -75,3 +75,15 @@ def test_gradient(oracle, name):
     # fp32 reference grads carry fp32 accumulation noise; low-precision ones were rounded to bf16/fp16
     tol = 1e-5 if g["logits_dtype"] == "float32" else 1e-2
     assert np.abs(grad - ref).max() <= tol * scale, (np.abs(grad - ref).max(), scale)
+
+
+@pytest.mark.parametrize("name", focal_names())
+def test_focal_loss_and_gradient(oracle, name):
+    """FocalLoss epilogue against the reference's own FocalLoss."""
+    g = load_focal(name)
+    dt = DT[g["logits_dtype"]]
+    loss, grad = oracle.focal_loss_and_grad(g["logits"], g["labels"], float(g["alpha"]), float(g["gamma"]),
+                                            bool(g["size_average"]), 255, dt)
+    assert abs(loss - float(g["loss"])) <= 2e-6 * abs(float(g["loss"]))
+    tol = 1e-5 if g["logits_dtype"] == "float32" else 1e-2
+    assert np.abs(grad - g["grad"]).max() <= tol * np.abs(g["grad"]).max()
