@@ -43,6 +43,11 @@ int make_logits_tmap(CUtensorMap* map, const void* logits, int ldtype, int plane
                      int box_c, int box_h, int box_w) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return SF_ERR_DRIVER;
+    // The encoder is a driver-API call: it needs the primary context current on THIS host thread.  A thread that has
+    // only ever been handed work (autograd's backward thread) may not have it bound yet -- seen under compute-sanitizer
+    // as CUDA_ERROR_INVALID_CONTEXT.  Bind it once per thread with a runtime call.
+    static thread_local bool ctx_bound = false;
+    if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; }
     const cuuint64_t esz = ldtype == SF_F32 ? 4 : 2;
     const CUtensorMapDataType dt = ldtype == SF_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                                  : ldtype == SF_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
@@ -51,9 +56,15 @@ int make_logits_tmap(CUtensorMap* map, const void* logits, int ldtype, int plane
     const cuuint64_t gstr[2] = {(cuuint64_t)w * esz, (cuuint64_t)w * h * esz};
     const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_c};
     const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = enc(map, dt, 3, const_cast<void*>(logits), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(map, dt, 3, const_cast<void*>(logits), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_ERROR_INVALID_CONTEXT || r == CUDA_ERROR_NOT_INITIALIZED) {
+        // The encoder is a driver-API call and needs the primary context current on THIS host thread; a thread that has
+        // only been handed work (autograd's backward thread) may not have it yet.  cudaFree(0) binds it; retry once.
+        cudaFree(nullptr);
+        r = enc(map, dt, 3, const_cast<void*>(logits), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     return r == CUDA_SUCCESS ? 0 : SF_ERR_DRIVER;
 }
 
