@@ -178,7 +178,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // FocalLoss (util/losses.py:17-25): f = a (1-pt)^g ce with pt = exp(-ce).  Returns f; *dfdce = a[(1-pt)^g + g ce pt (1-pt)^(g-1)].
 __device__ __forceinline__ float focal_value(float ce, float alpha, float gamma, float* dfdce) {
     const float pt = expf(-ce);
-    const float om = 1.0f - pt;
+    const float om = -expm1f(-ce);                                  // 1 - pt without the cancellation at small ce
     if (gamma == 0.0f) { *dfdce = alpha; return alpha * ce; }
     if (!(om > 0.0f)) { *dfdce = 0.0f; return 0.0f; }               // ce == 0 (also every ignored pixel)
     const float w = powf(om, gamma);
