@@ -126,6 +126,15 @@ int sf_ce_backward(const void* logits, int ldtype, const void* labels, int ydtyp
 int sf_hist_pairs(const void* a, int adtype, const long long* b, long long n, int C,
                   unsigned long long* mat, void* stream);
 
+/*
+ * Replaces the three tensor updates that follow every histogram in the reference -- `self.hist += bincount(...)`
+ * (util/metrics.py:27, float32 += int64) and `self.mat += bincount(...)` (util/utils.py:109) -- with one launch:
+ * hist_f32[k] = fl32(hist_f32[k] + fl32(counts[k])), hist_i64[k] += counts[k], mat[k] += counts[k], counts[k] = 0.
+ * Any of the three destinations may be NULL.  `counts` is the per-call matrix sf_eval_hist just filled.
+ */
+int sf_accumulate_counts(unsigned long long* counts, float* hist_f32, long long* hist_i64, long long* mat,
+                         int n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

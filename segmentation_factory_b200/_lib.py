@@ -18,7 +18,7 @@ SF_I64, SF_U8 = 0, 1
 # every symbol include/segfactory.h declares (tests/test_abi_symbols.py checks the .so exports them)
 SYMBOLS = (
     "sf_version", "sf_strerror", "sf_workspace_bytes", "sf_eval_hist", "sf_ce_forward",
-    "sf_loss_finalize", "sf_focal_finalize", "sf_ce_backward", "sf_hist_pairs",
+    "sf_loss_finalize", "sf_focal_finalize", "sf_ce_backward", "sf_hist_pairs", "sf_accumulate_counts",
 )
 
 _lib = None
@@ -48,7 +48,8 @@ def lib() -> ctypes.CDLL:
     L.sf_focal_finalize.argtypes = [vp, ll, f, f, i, vp, sz, vp, vp]
     L.sf_ce_backward.argtypes = [vp, i, vp, i, i, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp]
     L.sf_hist_pairs.argtypes = [vp, i, vp, ll, i, vp, vp]
-    for name in ("sf_eval_hist", "sf_ce_forward", "sf_loss_finalize", "sf_focal_finalize", "sf_ce_backward", "sf_hist_pairs"):
+    L.sf_accumulate_counts.argtypes = [vp, vp, vp, vp, i, vp]
+    for name in ("sf_eval_hist", "sf_ce_forward", "sf_loss_finalize", "sf_focal_finalize", "sf_ce_backward", "sf_hist_pairs", "sf_accumulate_counts"):
         getattr(L, name).restype = i
     _lib = L
     return L

@@ -140,6 +140,12 @@ int sf_ce_backward(const void* logits, int ldtype, const void* labels, int ydtyp
     return sf::launch_backward(a);
 }
 
+int sf_accumulate_counts(unsigned long long* counts, float* hist_f32, long long* hist_i64, long long* mat, int n,
+                         void* stream) {
+    if (!counts || n <= 0) return SF_ERR_ARG;
+    return sf::launch_accumulate_counts(counts, hist_f32, hist_i64, mat, n, stream);
+}
+
 int sf_hist_pairs(const void* a, int adtype, const long long* b, long long n, int C, unsigned long long* mat,
                   void* stream) {
     if (!a || !b || !mat || n < 0 || C <= 0) return SF_ERR_ARG;

@@ -41,6 +41,23 @@ hist_pairs_kernel(const void* __restrict__ a, int a_u8, const long long* __restr
     }
 }
 
+__global__ void accumulate_counts_kernel(unsigned long long* __restrict__ counts, float* __restrict__ hist_f32,
+                                         long long* __restrict__ hist_i64, long long* __restrict__ mat, int n) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const unsigned long long c = counts[k];
+        if (hist_f32) hist_f32[k] = __fadd_rn(hist_f32[k], __ull2float_rn(c));   // torch: float32 += int64 casts, then adds in fp32
+        if (hist_i64) hist_i64[k] += (long long)c;
+        if (mat) mat[k] += (long long)c;
+        counts[k] = 0ull;
+    }
+}
+
+int launch_accumulate_counts(unsigned long long* counts, float* hist_f32, long long* hist_i64, long long* mat, int n, void* stream) {
+    const int grid = std::min((n + 255) / 256, 64);
+    accumulate_counts_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(counts, hist_f32, hist_i64, mat, n);
+    return (int)cudaGetLastError();
+}
+
 int launch_hist_pairs(const void* a, int adtype, const long long* b, long long n, int C,
                       unsigned long long* mat, void* stream) {
     const size_t smem = (size_t)C * C * 4;

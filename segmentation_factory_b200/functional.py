@@ -92,6 +92,15 @@ def hist_pairs(a: torch.Tensor, b: torch.Tensor, C: int, mat: torch.Tensor) -> N
     _lib.check(rc, "sf_hist_pairs")
 
 
+def accumulate_counts(counts, hist_f32=None, hist_i64=None, mat=None) -> None:
+    """One launch for the per-call bookkeeping of Metrics / ConfusionMatrix: hist_f32 += counts (float32 += int64, the
+    reference's expression), hist_i64 += counts, mat += counts, counts = 0."""
+    with torch.cuda.device(counts.device):
+        rc = _lib.lib().sf_accumulate_counts(_ptr(counts), _ptr(hist_f32), _ptr(hist_i64), _ptr(mat), counts.numel(),
+                                             _stream(counts.device))
+    _lib.check(rc, "sf_accumulate_counts")
+
+
 class _FusedCE(torch.autograd.Function):
     """upsample + (OHEM) cross-entropy; forward = sf_ce_forward + sf_loss_finalize, backward = sf_ce_backward."""
 

@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 from torch import Tensor
 
-from .functional import eval_hist, hist_pairs
+from .functional import accumulate_counts, eval_hist, hist_pairs
 
 __all__ = ["Metrics", "ConfusionMatrix", "fused_eval_update"]
 
@@ -29,6 +29,7 @@ class Metrics:
         self.hist = torch.zeros(num_classes, num_classes).to(device)
         self.hist_i64 = torch.zeros(num_classes, num_classes, dtype=torch.int64).to(device)
         self.device = device
+        self._counts = None               # per-call matrix (device scratch, left zeroed by sf_accumulate_counts)
 
     def _accumulate(self, counts: Tensor) -> None:
         self.hist += counts                   # float32 += int64, exactly the reference's update expression
@@ -37,9 +38,14 @@ class Metrics:
     def update(self, pred: Tensor, target: Tensor, size=None) -> None:
         """pred: [B, C, h, w] logits at any resolution; target: [B, H, W] labels, or the flattened vector
         engine.py:91 passes (then H, W = `size`, defaulting to pred's own h, w)."""
-        counts = torch.zeros(self.num_classes, self.num_classes, dtype=torch.int64, device=pred.device)
+        counts = self._scratch(pred.device)
         eval_hist(pred, target, self.ignore_label, counts, size)
-        self._accumulate(counts)
+        accumulate_counts(counts, self.hist, self.hist_i64, None)
+
+    def _scratch(self, device):
+        if self._counts is None or self._counts.device != device:
+            self._counts = torch.zeros(self.num_classes, self.num_classes, dtype=torch.int64, device=device)
+        return self._counts
 
     def compute_iou(self):
         ious = self.hist.diag() / (self.hist.sum(0) + self.hist.sum(1) - self.hist.diag())
@@ -125,8 +131,7 @@ class ConfusionMatrix(object):
 def fused_eval_update(logits: Tensor, labels: Tensor, metric: Metrics, confmat: ConfusionMatrix, size=None) -> None:
     """One kernel launch feeding both accumulators of engine.evaluate (engine.py:90-91): the reference takes
     two argmax passes over materialised full-resolution logits and builds two histograms."""
-    counts = torch.zeros(metric.num_classes, metric.num_classes, dtype=torch.int64, device=logits.device)
+    counts = metric._scratch(logits.device)
     eval_hist(logits, labels, metric.ignore_label, counts, size)
-    metric._accumulate(counts)
     confmat._ensure(logits.device)
-    confmat.mat += counts
+    accumulate_counts(counts, metric.hist, metric.hist_i64, confmat.mat)     # 2 launches per batch in total
