@@ -159,7 +159,7 @@ def ce_loss_and_grad(logits, labels, ignore=255, class_w=None, ldtype=None, grad
     loss = ce_reduce(f["sums"])
     grad = None
     if want_grad:
-        coef = np.where(f["loss_px"] >= 0, np.float32(grad_out / f["sums"][1]), 0).astype(np.float32)
+        coef = np.full(f["loss_px"].shape, grad_out / f["sums"][1], np.float32)   # d mean / d loss_px = 1 / sum(w_y)
         grad = path_backward(logits, labels, f["lse_px"], coef, ignore, class_w, ldtype)
     return loss, grad
 
