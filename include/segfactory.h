@@ -101,9 +101,10 @@ int sf_loss_finalize(const float* loss_px, long long n_px, float ohem_thresh,
 /*
  * Replaces util/losses.py:9-25 (FocalLoss: alpha * (1 - exp(-ce))**gamma * ce, mean over ALL pixels or sum) on the
  * per-pixel cross-entropy sf_ce_forward wrote to loss_px (call it with ohem_thresh < 0 and class_w = NULL).
- * Writes sf_loss_state (branch 3) so that sf_ce_backward applies d focal / d ce per pixel.
+ * loss_px is OVERWRITTEN with d focal / d ce per pixel, which sf_ce_backward (sf_loss_state.branch == 3) then uses as
+ * the pixel's weight -- no transcendental work is added to the backward kernels.
  */
-int sf_focal_finalize(const float* loss_px, long long n_px, float alpha, float gamma, int size_average,
+int sf_focal_finalize(float* loss_px, long long n_px, float alpha, float gamma, int size_average,
                       void* workspace, size_t workspace_bytes, float* loss_out, void* stream);
 
 /*

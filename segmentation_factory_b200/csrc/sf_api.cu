@@ -121,7 +121,7 @@ int sf_loss_finalize(const float* loss_px, long long n_px, float ohem_thresh, vo
     return sf::launch_finalize(loss_px, n_px, ohem_thresh, workspace, loss_out, stream);
 }
 
-int sf_focal_finalize(const float* loss_px, long long n_px, float alpha, float gamma, int size_average, void* workspace,
+int sf_focal_finalize(float* loss_px, long long n_px, float alpha, float gamma, int size_average, void* workspace,
                       size_t workspace_bytes, float* loss_out, void* stream) {
     if (!workspace || !loss_px || n_px <= 0) return SF_ERR_ARG;
     if (workspace_bytes < sizeof(sf::Workspace)) return SF_ERR_WORKSPACE;

@@ -206,11 +206,9 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmap, const BwdParams p) {
             const long long y = ld_label(p.labels, p.label_u8, px);
             if (y != p.ignore && y >= 0 && y < p.C) {
                 float keep = 1.f;
-                if (branch == 3) {
-                    focal_value(__ldg(p.loss_px + px), stp->focal_alpha, stp->focal_gamma, &keep);   // d focal / d ce
-                } else if (branch != 0) {
+                if (branch != 0) {
                     const float l = __ldg(p.loss_px + px);
-                    keep = l > kth ? 1.f : (l == kth ? tie : 0.f);
+                    keep = branch == 3 ? l : (l > kth ? 1.f : (l == kth ? tie : 0.f));   // 3: loss_px holds d focal / d ce
                 }
                 const float wy = p.class_w ? __ldg(p.class_w + y) : 1.f;
                 coef = keep != 0.f ? keep * wy * gscale : 0.f;       // never 0 * inf

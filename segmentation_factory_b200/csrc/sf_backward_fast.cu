@@ -137,7 +137,8 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
 
     const sf_loss_state* stp = &p.ws->state;
     const int branch = stp->branch;
-    const float kth = stp->kth, tie = stp->tie_share, falpha = stp->focal_alpha, fgamma = stp->focal_gamma;
+    const float kth = stp->kth, tie = stp->tie_share;
+    const bool is_focal = branch == 3;
     const float gscale = (p.grad_out ? __ldg(p.grad_out) : 1.0f) * stp->inv_denom;
     const float2 l2e2 = splat(kLog2e);
 
@@ -239,8 +240,7 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
             // valid label: 0 <= y < C, y != ignore (64-bit labels: high word must be zero)
             const bool valid = alive && hi == 0 && (unsigned)lo < (unsigned)Ct && lo != ign;
             float keep = 1.f;
-            if (branch == 3) focal_value(loss, falpha, fgamma, &keep);            // FocalLoss: d focal / d ce
-            else if (has_loss) keep = loss > kth ? 1.f : (loss == kth ? tie : 0.f);
+            if (has_loss) keep = is_focal ? loss : (loss > kth ? 1.f : (loss == kth ? tie : 0.f));   // focal: loss_px holds d focal / d ce
             const float wy = cw_s[valid ? lo : 0];
             const float coef = (valid && keep != 0.f) ? keep * wy * gscale : 0.f;     // never 0 * inf
             if (__any_sync(0xffffffffu, coef != 0.f)) {

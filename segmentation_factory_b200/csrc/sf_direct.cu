@@ -203,8 +203,7 @@ bwd_direct_kernel(const DirParams p) {
             coef[v] = 0.f; cf[v] = 0.f; lse2[v] = 0.f; lab[v] = -1;
             if (y != p.ignore && y >= 0 && y < C) {
                 float keep = 1.f;
-                if (branch == 3) focal_value(__ldg(p.loss_in + px + v), stp->focal_alpha, stp->focal_gamma, &keep);
-                else if (branch != 0) { const float l = __ldg(p.loss_in + px + v); keep = l > kth ? 1.f : (l == kth ? tie : 0.f); }
+                if (branch != 0) { const float l = __ldg(p.loss_in + px + v); keep = branch == 3 ? l : (l > kth ? 1.f : (l == kth ? tie : 0.f)); }
                 if (keep != 0.f) {
                     const float lse = __ldg(p.lse_in + px + v);
                     coef[v] = keep * cw_s[(int)y] * gscale;

@@ -60,7 +60,6 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
     const int tx = tid % kFfTW, sy = tid / kFfTW;
     if (tid < 32) cw_s[tid] = (p.class_w && tid < C) ? __ldg(p.class_w + tid) : 1.0f;
     const bool want_hist = p.hist != nullptr;
-    const unsigned lane_lt = (1u << (tid & 31)) - 1u;              // lanes below mine: the leader of a match group has none
 
     if (want_hist)
         for (int k = tid; k < C * C; k += kFfThreads) hist_s[k] = 0;
@@ -158,15 +157,7 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
             const int cnt = TP::count(u, p.h);
             const int o0 = (i0 - ua) * G::BW, o1 = (i1 - ua) * G::BW;
             const int cj0 = j0 - jO, cj1 = j1 - jO;
-            const LT* q00 = Sg + o0 + cj0;                           // the four taps of channel 0; channel k adds k * PLANE
-            const LT* q01 = Sg + o0 + cj1;
-            const LT* q10 = Sg + o1 + cj0;
-            const LT* q11 = Sg + o1 + cj1;
-            const long long px0 = ((long long)b * p.H + TP::first(u)) * p.W + X;
-            float* loss_o = (p.loss_px && colok) ? p.loss_px + px0 : nullptr;   // running output pointers (no per-pixel 64-bit index)
-            float* lse_o = (p.lse_px && colok) ? p.lse_px + px0 : nullptr;
-            float lh1 = u < 0 ? 0.0f : 0.5f / S;                     // (r + 0.5) / S, exact increments
-            const float lh_step = u < 0 ? 0.0f : 1.0f / S;
+            long long px = ((long long)b * p.H + TP::first(u)) * p.W + X;
             float nanflag = 0.f;
             if (!SOFTMAX) {
                 #pragma unroll
@@ -174,7 +165,8 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
                 if (G::ODD) nanflag = __fmaf_rn(botl, 0.f, __fmaf_rn(topl, 0.f, nanflag));
             }
             #pragma unroll 1
-            for (int r = 0; r < cnt; ++r, labs >>= 8, lh1 += lh_step) {
+            for (int r = 0; r < cnt; ++r, px += p.W, labs >>= 8) {
+                const float lh1 = u < 0 ? 0.0f : ((float)r + 0.5f) * (1.0f / S);
                 const float lh0 = 1.0f - lh1;
                 const float2 lh0_2 = splat(lh0), lh1_2 = splat(lh1);
                 float2 z[NP > 0 ? NP : 1];
@@ -182,41 +174,28 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
                 #pragma unroll
                 for (int q = 0; q < NP; ++q) z[q] = rnd2<LT>(lerp2_pinned(top[q], lh0_2, bot[q], lh1_2));
                 if (G::ODD) zl = Logit<LT>::rnd(lerp_pinned(topl, lh0, botl, lh1));
-                // max as three independent FMNMX3 chains (ILP), then the lowest index that attains it (first-max rule of
-                // torch.argmax) as four independent select chains over channel ranges, merged with a min: the serial
-                // 9-deep max chain and 38-deep select chain were the longest dependency paths of a pixel
-                float pm0 = -INFINITY, pm1 = -INFINITY, pm2 = -INFINITY;
+                // max as a 3-input tree (FMNMX3), then the lowest index that attains it (first-max rule of torch.argmax)
+                float m = G::ODD ? zl : z[NP - 1].y;
                 #pragma unroll
-                for (int q = 0; q < NP; ++q) {
-                    const float t = fmaxf(z[q].x, z[q].y);
-                    if (q % 3 == 0) pm0 = fmaxf(pm0, t); else if (q % 3 == 1) pm1 = fmaxf(pm1, t); else pm2 = fmaxf(pm2, t);
-                }
-                float m = fmaxf(pm0, fmaxf(pm1, pm2));
-                if (G::ODD) m = fmaxf(m, zl);
-                constexpr int kNone = 1 << 20;
-                int ix0 = kNone, ix1 = kNone, ix2 = kNone, ix3 = G::ODD ? (zl == m ? C - 1 : kNone) : kNone;
+                for (int q = 0; q < NP; ++q) m = fmaxf(m, fmaxf(z[q].x, z[q].y));
+                int idx = C - 1;
                 #pragma unroll
                 for (int q = NP - 1; q >= 0; --q) {
-                    const int ch = NP >= 4 ? (q * 4) / NP : 0;
-                    if (ch == 0) { ix0 = (z[q].y == m) ? 2 * q + 1 : ix0; ix0 = (z[q].x == m) ? 2 * q : ix0; }
-                    else if (ch == 1) { ix1 = (z[q].y == m) ? 2 * q + 1 : ix1; ix1 = (z[q].x == m) ? 2 * q : ix1; }
-                    else if (ch == 2) { ix2 = (z[q].y == m) ? 2 * q + 1 : ix2; ix2 = (z[q].x == m) ? 2 * q : ix2; }
-                    else { ix3 = (z[q].y == m) ? 2 * q + 1 : ix3; ix3 = (z[q].x == m) ? 2 * q : ix3; }
+                    idx = (z[q].y == m) ? 2 * q + 1 : idx;
+                    idx = (z[q].x == m) ? 2 * q : idx;
                 }
-                int idx = min(min(ix0, ix1), min(ix2, ix3));
-                if (idx == kNone) idx = C - 1;                       // only when a NaN is involved (slow path below)
                 float ssum = 1.f;
                 const float m2 = __fmul_rn(m, kLog2e);
                 if (SOFTMAX) {
                     const float2 nm2 = splat(-m2);
-                    float2 a2 = make_float2(0.f, 0.f), b2 = make_float2(0.f, 0.f), c2 = make_float2(0.f, 0.f);
+                    float2 a2 = make_float2(0.f, 0.f), b2 = make_float2(0.f, 0.f);
                     #pragma unroll
                     for (int q = 0; q < NP; ++q) {
                         const float2 e = __ffma2_rn(z[q], l2e2, nm2);
                         const float2 ex = make_float2(ex2_approx(e.x), ex2_approx(e.y));
-                        if (q % 3 == 0) a2 = __fadd2_rn(a2, ex); else if (q % 3 == 1) b2 = __fadd2_rn(b2, ex); else c2 = __fadd2_rn(c2, ex);
+                        if (q & 1) b2 = __fadd2_rn(b2, ex); else a2 = __fadd2_rn(a2, ex);
                     }
-                    a2 = __fadd2_rn(__fadd2_rn(a2, b2), c2);
+                    a2 = __fadd2_rn(a2, b2);
                     ssum = a2.x + a2.y;
                     if (G::ODD) ssum += ex2_approx(__fmaf_rn(zl, kLog2e, -m2));
                 }
@@ -224,9 +203,9 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
                 if (weird) {                                         // torch: NaN beats everything, first NaN wins
                     #pragma unroll 1
                     for (int k = C - 1; k >= 0; --k) {
-                        const int ko = k * G::PLANE;
-                        const float t0 = lerp_pinned(Logit<LT>::ld(q00 + ko), lw0, Logit<LT>::ld(q01 + ko), lw1);
-                        const float t1 = lerp_pinned(Logit<LT>::ld(q10 + ko), lw0, Logit<LT>::ld(q11 + ko), lw1);
+                        const LT* qk = Sg + k * G::PLANE;
+                        const float t0 = lerp_pinned(Logit<LT>::ld(qk + o0 + cj0), lw0, Logit<LT>::ld(qk + o0 + cj1), lw1);
+                        const float t1 = lerp_pinned(Logit<LT>::ld(qk + o1 + cj0), lw0, Logit<LT>::ld(qk + o1 + cj1), lw1);
                         const float zk = Logit<LT>::rnd(lerp_pinned(t0, lh0, t1, lh1));
                         if (zk != zk) idx = k;
                     }
@@ -235,28 +214,26 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
                 const bool valid = lab != 255;
                 if (SOFTMAX && colok) {
                     const float corr = __fmaf_rn(m, kLog2e, -m2);          // exact residual of rn(m*log2e)
-                    float lg2v;
-                    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg2v) : "f"(ssum));    // ssum >= 1: no denormal path needed
-                    const float lg = (lg2v - corr) * kLn2;
+                    const float lg = (__log2f(ssum) - corr) * kLn2;
                     float l = 0.f;
                     if (valid) {
                         // label logit: same ops, same bits as the z[] entry of that channel
-                        const int ko = lab * G::PLANE;
-                        const float t0 = lerp_pinned(Logit<LT>::ld(q00 + ko), lw0, Logit<LT>::ld(q01 + ko), lw1);
-                        const float t1 = lerp_pinned(Logit<LT>::ld(q10 + ko), lw0, Logit<LT>::ld(q11 + ko), lw1);
+                        const LT* qk = Sg + lab * G::PLANE;
+                        const float t0 = lerp_pinned(Logit<LT>::ld(qk + o0 + cj0), lw0, Logit<LT>::ld(qk + o0 + cj1), lw1);
+                        const float t1 = lerp_pinned(Logit<LT>::ld(qk + o1 + cj0), lw0, Logit<LT>::ld(qk + o1 + cj1), lw1);
                         const float zy = Logit<LT>::rnd(lerp_pinned(t0, lh0, t1, lh1));
                         const float wy = cw_s[lab];
                         l = wy * (lg - (zy - m));
                         tile_loss += l; tile_w += wy; ++cnt_valid;
                         if (l > p.thresh) { tile_hard += l; ++cnt_hard; }
                     }
-                    if (loss_o) { *loss_o = l; loss_o += p.W; }
-                    if (lse_o) { *lse_o = m + lg; lse_o += p.W; }
+                    if (p.loss_px) p.loss_px[px] = l;
+                    if (p.lse_px) p.lse_px[px] = m + lg;
                 }
                 if (want_hist) {
                     const int key = (colok && valid) ? lab * C + idx : -1;
                     const unsigned peers = __match_any_sync(0xffffffffu, key);
-                    if (key >= 0 && (peers & lane_lt) == 0) atomicAdd(&hist_s[key], __popc(peers));
+                    if (key >= 0 && (int)(tid & 31) == __ffs(peers) - 1) atomicAdd(&hist_s[key], __popc(peers));
                 }
             }
         };

@@ -43,7 +43,7 @@ int launch_backward_direct(const BwdArgs& a);
 int launch_backward_fast(const BwdArgs& a);   // -1000: shape not covered
 
 int launch_finalize(const float* loss_px, long long n_px, float thresh, void* ws, float* loss_out, void* stream);
-int launch_focal(const float* loss_px, long long n_px, float alpha, float gamma, int size_average, void* ws,
+int launch_focal(float* loss_px, long long n_px, float alpha, float gamma, int size_average, void* ws,
                  float* loss_out, void* stream);
 int launch_accumulate_counts(unsigned long long* counts, float* hist_f32, long long* hist_i64, long long* mat, int n, void* stream);
 int launch_hist_pairs(const void* a, int adtype, const long long* b, long long n, int C,

@@ -184,7 +184,7 @@ finalize_kernel(const float* __restrict__ loss_px, long long n, float thresh, Wo
 // FocalLoss reduction (util/losses.py:17-25) over the per-pixel CE: one persistent pass, per-CTA partials in a fixed
 // order, the last CTA to finish (atomic ticket) sums them and writes the state -- deterministic, single launch.
 __global__ void __launch_bounds__(kSelThreads)
-focal_kernel(const float* __restrict__ ce, long long n, float alpha, float gamma, int size_average, Workspace* ws,
+focal_kernel(float* __restrict__ ce, long long n, float alpha, float gamma, int size_average, Workspace* ws,
              float* loss_out) {
     __shared__ double red[kSelThreads / 32];
     __shared__ bool last;
@@ -192,7 +192,8 @@ focal_kernel(const float* __restrict__ ce, long long n, float alpha, float gamma
     const long long stride = (long long)gridDim.x * kSelThreads;
     for (long long i = (long long)blockIdx.x * kSelThreads + threadIdx.x; i < n; i += stride) {
         float d;
-        a += (double)focal_value(__ldg(ce + i), alpha, gamma, &d);
+        a += (double)focal_value(ce[i], alpha, gamma, &d);
+        ce[i] = d;                                                   // loss_px now holds d focal / d ce: the backward's per-pixel weight
     }
     const double cta = block_sum<kSelThreads>(a, red);
     if (threadIdx.x == 0) {
@@ -218,7 +219,7 @@ focal_kernel(const float* __restrict__ ce, long long n, float alpha, float gamma
     }
 }
 
-int launch_focal(const float* loss_px, long long n_px, float alpha, float gamma, int size_average, void* ws,
+int launch_focal(float* loss_px, long long n_px, float alpha, float gamma, int size_average, void* ws,
                  float* loss_out, void* stream) {
     Workspace* w = reinterpret_cast<Workspace*>(ws);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
