@@ -15,6 +15,8 @@
 //   * label / lse / loss of the next row are prefetched while the current row is computed;
 //   * rows in which no lane of a warp holds a kept pixel skip the channel loop (ignored labels, OHEM drops).
 #include "sf_fast.cuh"
+#include <cstdlib>
+
 #include "sf_launch.h"
 
 namespace sf {
@@ -327,7 +329,8 @@ static int bf_launch(const BwdArgs& a) {
     CUtensorMap tmap{};
     const int rc = make_logits_tmap(&tmap, a.logits, a.ldtype, a.B * a.C, a.h, a.w, C, kBfBH, G::BW);
     if (rc != 0) return rc;
-    const size_t smem = (size_t)G::SRC_BYTES + (size_t)2 * C * kBfThreads * 4 + 16;
+    size_t smem = (size_t)G::SRC_BYTES + (size_t)2 * C * kBfThreads * 4 + 16;
+    if (const char* pad = std::getenv("SF_DEBUG_SMEM_PAD_KB")) smem += (size_t)atoi(pad) * 1024;   // experiment knob (occupancy sensitivity)
     auto k = bwd_fast_kernel<LT, C, S, CHUNK>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;

@@ -13,6 +13,8 @@
 // Tile = 64 columns x 4 strips x GPS groups; one TMA box [C][4*GPS+1][BW] per tile, 2-stage mbarrier pipeline,
 // persistent CTAs (2 per SM).
 #include "sf_fast.cuh"
+#include <cstdlib>
+
 #include "sf_launch.h"
 
 namespace sf {
@@ -324,7 +326,9 @@ static int ff_launch(const FwdArgs& a) {
     auto k = fwd_fast_kernel<LT, C, S, SOFTMAX>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    const int grid = (int)std::min<long long>(total, std::min(kMaxCtas, 2 * sm_count()));
+    const char* gm = std::getenv("SF_DEBUG_CTAS_PER_SM");             // experiment knob (occupancy sensitivity)
+    const int per_sm = gm ? std::max(1, atoi(gm)) : 2;
+    const int grid = (int)std::min<long long>(total, std::min(kMaxCtas, per_sm * sm_count()));
     k<<<grid, kFfThreads, smem, reinterpret_cast<cudaStream_t>(a.stream)>>>(tmap, p);
     return (int)cudaGetLastError();
 }
