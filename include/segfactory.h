@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SF_VERSION 100            /* 0.1.0 */
+#define SF_VERSION 101            /* 0.1.1 */
 
 enum sf_dtype       { SF_F32 = 0, SF_BF16 = 1, SF_F16 = 2 };     /* logits / gradient element type */
 enum sf_label_dtype { SF_I64 = 0, SF_U8 = 1 };                   /* datasets/*.py: int64, Kvasir uint8 */
@@ -118,6 +118,50 @@ int sf_ce_backward(const void* logits, int ldtype, const void* labels, int ydtyp
                    const float* class_w, const float* loss_px, const float* lse_px,
                    const float* grad_out, const void* workspace,
                    void* grad_logits, void* stream);
+
+/*
+ * Dice term of engine.criterion (engine.py:10-15: loss = F.cross_entropy(...) + dice_loss(softmax(x), build_target(...),
+ * multiclass=True, ignore_index); util/losses.py:126-177), fused with the CE path above.  Call order for one step:
+ *   sf_ce_forward(ohem_thresh < 0, lse_px != NULL) -> sf_loss_finalize -> sf_dice_stats -> sf_dice_finalize
+ *   [-> sf_dice_coef -> sf_dice_backward when a gradient is wanted].
+ * dice_ws is caller-owned device scratch of sf_dice_workspace_bytes(B, C) bytes; its first bytes are an sf_dice_state.
+ */
+typedef struct sf_dice_state {
+    float   dice_loss;    /* 1 - mean over (image, class) of the dice coefficient              */
+    float   total_loss;   /* CE (sf_loss_state.loss of `workspace`, 0 if NULL) + dice_loss      */
+    int32_t B, C;
+    float   epsilon;
+    int32_t reserved[11];
+} sf_dice_state;
+
+size_t sf_dice_workspace_bytes(int B, int C);
+
+/* Per image and class over the non-ignored pixels: sum softmax_c, sum softmax_c [y == c], count [y == c]
+ * (the three sums dice_coeff, util/losses.py:139-158, takes with masked gathers, dot and sum).  lse_px from sf_ce_forward. */
+int sf_dice_stats(const void* logits, int ldtype, const void* labels, int ydtype,
+                  int B, int C, int h, int w, int H, int W, int ignore,
+                  const float* lse_px, void* dice_ws, size_t dice_ws_bytes, void* stream);
+
+/* D = (2 inter + eps) / (sets + eps), sets == 0 -> sets = 2 inter (util/losses.py:152-155); dice loss = 1 - mean D
+ * (:161-177).  Writes sf_dice_state and, when loss_out != NULL, CE + dice to *loss_out (device fp32). */
+int sf_dice_finalize(int B, int C, float epsilon, const void* workspace, void* dice_ws, size_t dice_ws_bytes,
+                     float* loss_out, void* stream);
+
+/* Per-pixel scalars of the fused CE + dice gradient  d L / d z_k = p_k (A + tb[b][k]) - [k == y] Bc :
+ * coef_b_px = w_y / sum(w) + ta[b][y] p_y,  coef_a_px = coef_b_px - sum_j tb[b][j] p_j;  both [B*H*W] fp32, 0 where ignored.
+ * workspace NULL: dice gradient only. */
+int sf_dice_coef(const void* logits, int ldtype, const void* labels, int ydtype,
+                 int B, int C, int h, int w, int H, int W, int ignore,
+                 const float* class_w, const float* lse_px, const void* workspace,
+                 const void* dice_ws, size_t dice_ws_bytes, float* coef_a_px, float* coef_b_px, void* stream);
+
+/* Replaces autograd of engine.criterion through softmax, cross_entropy and the bilinear upsample; same gather form and
+ * conventions as sf_ce_backward. */
+int sf_dice_backward(const void* logits, int ldtype, const void* labels, int ydtype,
+                     int B, int C, int h, int w, int H, int W, int ignore,
+                     const float* lse_px, const float* coef_a_px, const float* coef_b_px,
+                     const void* dice_ws, size_t dice_ws_bytes, const float* grad_out,
+                     void* grad_logits, void* stream);
 
 /*
  * Replaces ConfusionMatrix.update(a, b) (util/utils.py:99-109) when the caller already holds the

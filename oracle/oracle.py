@@ -43,6 +43,8 @@ def lib():
         L.orc_ohem_reduce.argtypes = [vp, ctypes.c_int64, ctypes.c_int64, f, vp, vp, vp, vp]
         L.orc_path_backward.argtypes = [vp, i, vp, i, i, i, i, i, i, i, i, vp, vp, vp, vp]
         L.orc_hist_pairs.argtypes = [vp, vp, ctypes.c_int64, i, vp]
+        L.orc_dice_stats.argtypes = [vp, i, vp, i, i, i, i, i, i, i, i, vp, vp]
+        L.orc_dice_backward.argtypes = [vp, i, vp, i, i, i, i, i, i, i, i, vp, vp, ctypes.c_double, vp, vp, vp]
         L.orc_num_threads.restype = i
         _lib = L
     return _lib
@@ -202,3 +204,55 @@ def focal_loss_and_grad(logits, labels, alpha=1.0, gamma=0.0, size_average=True,
         coef = (alpha * (w + ce * dw) / denom).astype(np.float32)
         grad = path_backward(logits, labels, f["lse_px"], coef, ignore, None, ldtype)
     return loss, grad
+
+
+def dice_stats(logits, labels, lse_px, ignore=255, ldtype=None) -> np.ndarray:
+    """[B, C, 3] double: sum p_c, sum p_c [y == c], count [y == c] over the non-ignored pixels of each image."""
+    logits = np.ascontiguousarray(logits)
+    labels = np.ascontiguousarray(labels)
+    B, C, h, w = logits.shape
+    _, H, W = labels.shape
+    stats = np.zeros((B, C, 3), np.float64)
+    rc = lib().orc_dice_stats(_p(logits), logits_code(logits, ldtype), _p(labels), labels_code(labels),
+                              B, C, h, w, H, W, int(ignore), _p(np.ascontiguousarray(lse_px, np.float32)), _p(stats))
+    assert rc == 0
+    return stats
+
+
+def dice_from_stats(stats: np.ndarray, eps: float = 1e-6):
+    """util/losses.py:147-177 on the per-image sums: returns (dice_loss, ta, tb) with the backward tables of
+    orc_dice_backward (zero where sets_sum == 0 makes the coefficient a constant)."""
+    B, C, _ = stats.shape
+    sp, si, sn = stats[..., 0], stats[..., 1], stats[..., 2]
+    sets = sp + sn
+    dead = sets == 0
+    den = np.where(dead, 2 * si, sets) + eps
+    D = (2 * si + eps) / den
+    loss = 1.0 - D.sum() / (B * C)
+    ta = np.where(dead, 0.0, 2.0 / den) / (B * C)
+    tb = np.where(dead, 0.0, D / den) / (B * C)
+    return float(loss), np.ascontiguousarray(ta), np.ascontiguousarray(tb)
+
+
+def criterion_loss_and_grad(logits, labels, class_w=None, dice=True, ignore=255, ldtype=None, want_grad=True, eps=1e-6):
+    """engine.criterion (engine.py:10-15): mean CE (+ multiclass dice loss) through the low-res logits."""
+    f = path_forward(logits, labels, ignore, class_w, 0.0, ldtype, want_arg=False, want_hist=False)
+    ce = ce_reduce(f["sums"])
+    if not dice:
+        loss, grad = ce_loss_and_grad(logits, labels, ignore, class_w, ldtype, want_grad=want_grad)
+        return loss, grad, None
+    stats = dice_stats(logits, labels, f["lse_px"], ignore, ldtype)
+    dl, ta, tb = dice_from_stats(stats, eps)
+    grad = None
+    if want_grad:
+        logits_c = np.ascontiguousarray(logits)
+        labels_c = np.ascontiguousarray(labels)
+        B, C, h, w = logits_c.shape
+        _, H, W = labels_c.shape
+        grad = np.empty((B, C, h, w), np.float32)
+        cw = None if class_w is None else np.ascontiguousarray(class_w, np.float32)
+        rc = lib().orc_dice_backward(_p(logits_c), logits_code(logits_c, ldtype), _p(labels_c), labels_code(labels_c),
+                                     B, C, h, w, H, W, int(ignore), _p(cw), _p(f["lse_px"]),
+                                     1.0 / f["sums"][1], _p(ta), _p(tb), _p(grad))
+        assert rc == 0
+    return ce + dl, grad, dict(stats=stats, ce=ce, dice=dl)

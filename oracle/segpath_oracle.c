@@ -17,6 +17,7 @@
  *   util/metrics.py:24-27       Metrics.update (argmax -> bincount)            -> orc_path_forward (hist)
  *   util/utils.py:99-109        ConfusionMatrix.update                         -> orc_hist_pairs
  *   autograd of the above                                                      -> orc_path_backward
+ *   engine.py:10-15 criterion: CE + dice_loss (util/losses.py:126-177)         -> orc_dice_stats, orc_dice_backward
  *
  * The arithmetic lives in PyTorch ATen (reference pin torch==2.0.1; this image 2.11.0).
  * Bilinear rule, established by differential probing of torch CPU (generic NCHW kernel,
@@ -293,6 +294,103 @@ int orc_path_backward(const void* logits, int ldtype, const void* labels, int yd
         free(acc);
     }
     free(ty); free(tx);
+    return 0;
+}
+
+/*
+ * Dice term of engine.criterion (engine.py:10-15 -> util/losses.py:126-177, multiclass=True):
+ *   p = softmax(upsampled logits); per image b and class c over the pixels whose label != ignore (build_target
+ *   paints every channel of an ignored pixel with ignore_index, dice_coeff masks them out):
+ *     inter = sum p_c [y == c];  sets = sum p_c + sum [y == c];  if sets == 0: sets = 2 inter
+ *     D_bc = (2 inter + eps) / (sets + eps);   loss = 1 - mean_bc D_bc
+ * stats [B][C][3] double = {sum p_c, inter, count[y == c]}; overwritten.
+ */
+int orc_dice_stats(const void* logits, int ldtype, const void* labels, int ydtype,
+                   int B, int C, int h, int w, int H, int W, int ignore,
+                   const float* lse_px, double* stats) {
+    orc_tap* ty = (orc_tap*)malloc(sizeof(orc_tap) * (size_t)H);
+    orc_tap* tx = (orc_tap*)malloc(sizeof(orc_tap) * (size_t)W);
+    if (!ty || !tx) return -1;
+    make_taps(h, H, ldtype, ty); make_taps(w, W, ldtype, tx);
+    #pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t bc = 0; bc < (int64_t)B * C; ++bc) {
+        const int b = (int)(bc / C), c = (int)(bc % C);
+        double sp = 0.0, si = 0.0, sn = 0.0;
+        for (int Y = 0; Y < H; ++Y)
+            for (int X = 0; X < W; ++X) {
+                const int64_t px = ((int64_t)b * H + Y) * W + X;
+                const int64_t y = load_label(labels, ydtype, px);
+                if (y == ignore || y < 0 || y >= C) continue;
+                const float zc = interp_one(logits, ldtype, bc * h * w, w, &ty[Y], &tx[X]);
+                const double p = exp((double)zc - (double)lse_px[px]);
+                sp += p;
+                if (y == c) { si += p; sn += 1.0; }
+            }
+        stats[bc * 3 + 0] = sp; stats[bc * 3 + 1] = si; stats[bc * 3 + 2] = sn;
+    }
+    free(ty); free(tx);
+    return 0;
+}
+
+/*
+ * Backward of  ce_scale * sum_px w_y (lse - z_y)  +  (1 - mean_bc D_bc)  through softmax and the bilinear resize.
+ *   d(-mean D)/d p_c(px) = -(ta_bc [y == c] - tb_bc),   ta = 2 / (BC (sets+eps)),  tb = D / (BC (sets+eps))
+ *   through softmax:  d/d z_k = p_k (A + tb_k) - [k == y] Bc,   Bc = ce_scale w_y + ta_y p_y,   A = Bc - sum_j tb_j p_j
+ * ta, tb: [B][C] double (0 where the reference's sets == 0 branch makes D constant).
+ */
+int orc_dice_backward(const void* logits, int ldtype, const void* labels, int ydtype,
+                      int B, int C, int h, int w, int H, int W, int ignore,
+                      const float* class_w, const float* lse_px, double ce_scale,
+                      const double* ta, const double* tb, float* grad) {
+    orc_tap* ty = (orc_tap*)malloc(sizeof(orc_tap) * (size_t)H);
+    orc_tap* tx = (orc_tap*)malloc(sizeof(orc_tap) * (size_t)W);
+    const int64_t n = (int64_t)B * H * W;
+    double* cA = (double*)malloc(sizeof(double) * (size_t)n);
+    double* cB = (double*)malloc(sizeof(double) * (size_t)n);
+    if (!ty || !tx || !cA || !cB) return -1;
+    make_taps(h, H, ldtype, ty); make_taps(w, W, ldtype, tx);
+    #pragma omp parallel for schedule(static)
+    for (int64_t px = 0; px < n; ++px) {
+        cA[px] = 0.0; cB[px] = 0.0;
+        const int64_t y = load_label(labels, ydtype, px);
+        if (y == ignore || y < 0 || y >= C) continue;
+        const int b = (int)(px / ((int64_t)H * W)), Y = (int)(px / W % H), X = (int)(px % W);
+        double G = 0.0, py = 0.0;
+        for (int c = 0; c < C; ++c) {
+            const float zc = interp_one(logits, ldtype, ((int64_t)b * C + c) * h * w, w, &ty[Y], &tx[X]);
+            const double p = exp((double)zc - (double)lse_px[px]);
+            G += tb[b * C + c] * p;
+            if (c == y) py = p;
+        }
+        const double wy = class_w ? (double)class_w[y] : 1.0;
+        cB[px] = ce_scale * wy + ta[b * C + y] * py;
+        cA[px] = cB[px] - G;
+    }
+    #pragma omp parallel
+    {
+        double* acc = (double*)malloc(sizeof(double) * (size_t)h * w);
+        #pragma omp for schedule(dynamic, 1)
+        for (int64_t bc = 0; bc < (int64_t)B * C; ++bc) {
+            const int b = (int)(bc / C), c = (int)(bc % C);
+            memset(acc, 0, sizeof(double) * (size_t)h * w);
+            for (int Y = 0; Y < H; ++Y)
+                for (int X = 0; X < W; ++X) {
+                    const int64_t px = ((int64_t)b * H + Y) * W + X;
+                    const int64_t y = load_label(labels, ydtype, px);
+                    if (y == ignore || y < 0 || y >= C) continue;
+                    const float zc = interp_one(logits, ldtype, bc * h * w, w, &ty[Y], &tx[X]);
+                    const double p = exp((double)zc - (double)lse_px[px]);
+                    const double g = p * (cA[px] + tb[bc]) - (c == y ? cB[px] : 0.0);
+                    acc[ty[Y].i0 * w + tx[X].i0] += g * ty[Y].l0 * tx[X].l0;
+                    acc[ty[Y].i0 * w + tx[X].i1] += g * ty[Y].l0 * tx[X].l1;
+                    acc[ty[Y].i1 * w + tx[X].i0] += g * ty[Y].l1 * tx[X].l0;
+                    acc[ty[Y].i1 * w + tx[X].i1] += g * ty[Y].l1 * tx[X].l1;
+                }
+            for (int k = 0; k < h * w; ++k) grad[bc * h * w + k] = (float)acc[k];
+        }
+        free(acc);
+    }
+    free(ty); free(tx); free(cA); free(cB);
     return 0;
 }
 

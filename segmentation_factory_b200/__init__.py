@@ -4,12 +4,14 @@ Mirrors the reference's util/ API for this path only:
     CrossEntropy, OhemCrossEntropy, get_loss        (util/losses.py)
     Metrics                                         (util/metrics.py)
     ConfusionMatrix                                 (util/utils.py)
+    criterion (CE + dice)                           (engine.py:10-15)
 backed by hand-written sm_100a kernels in libsegfactory.so (C ABI: include/segfactory.h).
 """
 from .losses import CrossEntropy, FocalLoss, OhemCrossEntropy, get_loss
 from .metrics import ConfusionMatrix, Metrics, fused_eval_update
-from .functional import eval_hist, fused_cross_entropy, fused_focal_loss, hist_pairs
+from .engine import criterion
+from .functional import eval_hist, fused_criterion, fused_cross_entropy, fused_focal_loss, hist_pairs
 
 __all__ = ["CrossEntropy", "OhemCrossEntropy", "FocalLoss", "fused_focal_loss", "get_loss", "Metrics", "ConfusionMatrix",
-           "fused_eval_update", "fused_cross_entropy", "eval_hist", "hist_pairs"]
+           "fused_eval_update", "fused_cross_entropy", "fused_criterion", "criterion", "eval_hist", "hist_pairs"]
 __version__ = "0.1.0"

@@ -140,6 +140,56 @@ int sf_ce_backward(const void* logits, int ldtype, const void* labels, int ydtyp
     return sf::launch_backward(a);
 }
 
+size_t sf_dice_workspace_bytes(int B, int C) { return (B > 0 && C > 0) ? sf::dice_ws_bytes(B, C) : 0; }
+
+static sf::FwdArgs dice_args(const void* logits, int ldtype, const void* labels, int ydtype, int B, int C, int h, int w,
+                             int H, int W, int ignore, void* stream) {
+    sf::FwdArgs a{};
+    a.logits = logits; a.ldtype = ldtype; a.labels = labels; a.ydtype = ydtype;
+    a.B = B; a.C = C; a.h = h; a.w = w; a.H = H; a.W = W; a.ignore = ignore;
+    a.stream = stream; a.softmax = true; a.force_no_tma = sf::env_no_tma();
+    return a;
+}
+
+int sf_dice_stats(const void* logits, int ldtype, const void* labels, int ydtype, int B, int C, int h, int w, int H,
+                  int W, int ignore, const float* lse_px, void* dice_ws, size_t dice_ws_bytes, void* stream) {
+    if (!lse_px || !dice_ws || B <= 0 || C <= 0) return SF_ERR_ARG;
+    if (dice_ws_bytes < sf::dice_ws_bytes(B, C)) return SF_ERR_WORKSPACE;
+    if ((uintptr_t)dice_ws % 8) return SF_ERR_ALIGN;
+    return sf::launch_dice_stats(dice_args(logits, ldtype, labels, ydtype, B, C, h, w, H, W, ignore, stream), lse_px, dice_ws);
+}
+
+int sf_dice_finalize(int B, int C, float epsilon, const void* workspace, void* dice_ws, size_t dice_ws_bytes,
+                     float* loss_out, void* stream) {
+    if (!dice_ws || B <= 0 || C <= 0 || (long long)B * C >= (1LL << 24)) return SF_ERR_ARG;
+    if (dice_ws_bytes < sf::dice_ws_bytes(B, C)) return SF_ERR_WORKSPACE;
+    return sf::launch_dice_finalize(B, C, epsilon, workspace, dice_ws, loss_out, stream);
+}
+
+int sf_dice_coef(const void* logits, int ldtype, const void* labels, int ydtype, int B, int C, int h, int w, int H,
+                 int W, int ignore, const float* class_w, const float* lse_px, const void* workspace,
+                 const void* dice_ws, size_t dice_ws_bytes, float* coef_a_px, float* coef_b_px, void* stream) {
+    if (!lse_px || !dice_ws || !coef_a_px || !coef_b_px || B <= 0 || C <= 0) return SF_ERR_ARG;
+    if (dice_ws_bytes < sf::dice_ws_bytes(B, C)) return SF_ERR_WORKSPACE;
+    sf::FwdArgs a = dice_args(logits, ldtype, labels, ydtype, B, C, h, w, H, W, ignore, stream);
+    a.class_w = class_w; a.ws = const_cast<void*>(workspace);
+    return sf::launch_dice_coef(a, lse_px, dice_ws, coef_a_px, coef_b_px);
+}
+
+int sf_dice_backward(const void* logits, int ldtype, const void* labels, int ydtype, int B, int C, int h, int w, int H,
+                     int W, int ignore, const float* lse_px, const float* coef_a_px, const float* coef_b_px,
+                     const void* dice_ws, size_t dice_ws_bytes, const float* grad_out, void* grad_logits, void* stream) {
+    if (!lse_px || !dice_ws || !coef_a_px || !coef_b_px || !grad_logits || B <= 0 || C <= 0) return SF_ERR_ARG;
+    if (dice_ws_bytes < sf::dice_ws_bytes(B, C)) return SF_ERR_WORKSPACE;
+    sf::BwdArgs a{};
+    a.logits = logits; a.ldtype = ldtype; a.labels = labels; a.ydtype = ydtype;
+    a.B = B; a.C = C; a.h = h; a.w = w; a.H = H; a.W = W; a.ignore = ignore;
+    a.lse_px = lse_px; a.grad_out = grad_out; a.coef_a = coef_a_px; a.coef_b = coef_b_px;
+    a.dice_tb = sf::dice_tb_table(dice_ws, B, C);
+    a.grad_logits = grad_logits; a.stream = stream; a.force_no_tma = sf::env_no_tma();
+    return sf::launch_backward(a);
+}
+
 int sf_accumulate_counts(unsigned long long* counts, float* hist_f32, long long* hist_i64, long long* mat, int n,
                          void* stream) {
     if (!counts || n <= 0) return SF_ERR_ARG;

@@ -36,6 +36,9 @@ struct BwdParams {
     const float* lse_px;
     const float* grad_out;
     const Workspace* ws;
+    const float* coef_a;                     // DICE: per-pixel A and Bc of sf_dice.cu (d/dz_k = p_k (A + tb_k) - [k == y] Bc)
+    const float* coef_b;
+    const float* dice_tb;                    // DICE: [B][C]
     void* grad;
     Axis ay, ax;
     int B, C, ignore, label_u8;
@@ -62,7 +65,7 @@ __device__ __forceinline__ void onehot_sub(int yk, float (&a0)[NCH], float (&a1)
 #undef SF_CASE
 }
 
-template <typename LT, int NCH>
+template <typename LT, int NCH, bool DICE>
 __global__ void __launch_bounds__(kBwdThreads, 2)
 bwd_kernel(const __grid_constant__ CUtensorMap tmap, const BwdParams p) {
     static_assert(NCH <= 24, "onehot_sub covers 24 channels per chunk");
@@ -133,10 +136,16 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmap, const BwdParams p) {
     const int j0l = tc.i0 - jO, j1l = tc.i1 - jO;
     const float lw0 = tc.l0, lw1 = tc.l1;
 
-    const sf_loss_state* stp = &p.ws->state;
-    const int branch = stp->branch;
-    const float kth = stp->kth, tie = stp->tie_share;
-    const float gscale = (p.grad_out ? __ldg(p.grad_out) : 1.0f) * stp->inv_denom;
+    int branch = 0;
+    float kth = 0.f, tie = 0.f;
+    float gscale = p.grad_out ? __ldg(p.grad_out) : 1.0f;
+    if (!DICE) {
+        const sf_loss_state* stp = &p.ws->state;
+        branch = stp->branch; kth = stp->kth; tie = stp->tie_share;
+        gscale *= stp->inv_denom;
+    }
+    __shared__ float kb_s[24];                                      // DICE: tb[b][c0 .. c0+NCH) (LDS broadcast in the row loop)
+    if (DICE && tid < NCH) kb_s[tid] = tid < nvalid ? __ldg(p.dice_tb + (long long)b * p.C + c0 + tid) : 0.f;
 
     __syncthreads();
     if (p.use_tma) mbar_wait(bar, 0);
@@ -199,36 +208,52 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmap, const BwdParams p) {
             loaded = true;
         }
         // ---- per-pixel coefficient ----
-        float coef = 0.f, lse = 0.f;
+        float coef = 0.f, lse = 0.f, cb = 0.f;
         int yk = -1;
+        bool live = false;
         if (colok) {
             const long long px = ((long long)b * p.ay.out + Y) * p.ax.out + X;
             const long long y = ld_label(p.labels, p.label_u8, px);
             if (y != p.ignore && y >= 0 && y < p.C) {
-                float keep = 1.f;
-                if (branch != 0) {
-                    const float l = __ldg(p.loss_px + px);
-                    keep = branch == 3 ? l : (l > kth ? 1.f : (l == kth ? tie : 0.f));   // 3: loss_px holds d focal / d ce
+                if (DICE) {
+                    coef = __ldg(p.coef_a + px) * gscale;
+                    cb = __ldg(p.coef_b + px) * gscale;
+                    lse = __ldg(p.lse_px + px); yk = (int)y - c0; live = true;
+                } else {
+                    float keep = 1.f;
+                    if (branch != 0) {
+                        const float l = __ldg(p.loss_px + px);
+                        keep = branch == 3 ? l : (l > kth ? 1.f : (l == kth ? tie : 0.f));   // 3: loss_px holds d focal / d ce
+                    }
+                    const float wy = p.class_w ? __ldg(p.class_w + y) : 1.f;
+                    coef = keep != 0.f ? keep * wy * gscale : 0.f;       // never 0 * inf
+                    if (coef != 0.f) { lse = __ldg(p.lse_px + px); yk = (int)y - c0; live = true; }
                 }
-                const float wy = p.class_w ? __ldg(p.class_w + y) : 1.f;
-                coef = keep != 0.f ? keep * wy * gscale : 0.f;       // never 0 * inf
-                if (coef != 0.f) { lse = __ldg(p.lse_px + px); yk = (int)y - c0; }
             }
         }
-        if (__any_sync(0xffffffffu, coef != 0.f)) {
-            if (coef != 0.f) {
+        if (__any_sync(0xffffffffu, live)) {
+            if (live) {
                 const float lse2 = __fmul_rn(lse, kLog2e);
                 const float corr = __fmaf_rn(lse, kLog2e, -lse2);          // exact residual of rn(lse*log2e)
-                const float cf = coef * __fmaf_rn(-corr, kLn2, 1.0f);      // 2^-corr to first order
+                const float pf = __fmaf_rn(-corr, kLn2, 1.0f);             // 2^-corr to first order
+                const float cf = coef * pf;
+                if (!DICE) cb = coef;
                 float lh0 = ty.l0, lh1 = ty.l1;
-                float v0 = cf * lh0, v1 = cf * lh1, o0 = coef * lh0, o1 = coef * lh1;
-                if (ty.i1 == ty.i0) { v0 += v1; v1 = 0.f; o0 += o1; o1 = 0.f; }   // clamped bottom row / identity
+                float v0 = cf * lh0, v1 = cf * lh1, o0 = cb * lh0, o1 = cb * lh1;
+                float u0 = DICE ? gscale * pf * lh0 : 0.f, u1 = DICE ? gscale * pf * lh1 : 0.f;
+                if (ty.i1 == ty.i0) { v0 += v1; v1 = 0.f; o0 += o1; o1 = 0.f; u0 += u1; u1 = 0.f; }   // clamped bottom row / identity
                 #pragma unroll
                 for (int k = 0; k < NCH; ++k) {
                     const float z = Logit<LT>::rnd(lerp_pinned(tt[k], lh0, tb[k], lh1));
                     const float pc = ex2_approx(__fmaf_rn(z, kLog2e, -lse2));
-                    acc0[k] = fmaf(pc, v0, acc0[k]);
-                    acc1[k] = fmaf(pc, v1, acc1[k]);
+                    if (DICE) {
+                        const float kbk = kb_s[k];
+                        acc0[k] = fmaf(pc, fmaf(kbk, u0, v0), acc0[k]);
+                        acc1[k] = fmaf(pc, fmaf(kbk, u1, v1), acc1[k]);
+                    } else {
+                        acc0[k] = fmaf(pc, v0, acc0[k]);
+                        acc1[k] = fmaf(pc, v1, acc1[k]);
+                    }
                 }
                 if (yk >= 0 && yk < nvalid) onehot_sub<NCH>(yk, acc0, acc1, o0, o1);
             }
@@ -246,9 +271,9 @@ static int pick_nch_bwd(int C) {
     return pad8 < pad16 ? 8 : 16;
 }
 
-template <typename LT, int NCH>
+template <typename LT, int NCH, bool DICE>
 static int launch_bwd_one(const CUtensorMap& tmap, const BwdParams& p, int grid, size_t smem, cudaStream_t st) {
-    auto k = bwd_kernel<LT, NCH>;
+    auto k = bwd_kernel<LT, NCH, DICE>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     k<<<grid, kBwdThreads, smem, st>>>(tmap, p);
@@ -257,10 +282,17 @@ static int launch_bwd_one(const CUtensorMap& tmap, const BwdParams& p, int grid,
 
 template <typename LT>
 static int launch_bwd_nch(int nch, const CUtensorMap& tmap, const BwdParams& p, int grid, size_t smem, cudaStream_t st) {
+    if (p.coef_a) {
+        switch (nch) {
+            case 19: return launch_bwd_one<LT, 19, true>(tmap, p, grid, smem, st);
+            case 16: return launch_bwd_one<LT, 16, true>(tmap, p, grid, smem, st);
+            default: return launch_bwd_one<LT, 8, true>(tmap, p, grid, smem, st);
+        }
+    }
     switch (nch) {
-        case 19: return launch_bwd_one<LT, 19>(tmap, p, grid, smem, st);
-        case 16: return launch_bwd_one<LT, 16>(tmap, p, grid, smem, st);
-        default: return launch_bwd_one<LT, 8>(tmap, p, grid, smem, st);
+        case 19: return launch_bwd_one<LT, 19, false>(tmap, p, grid, smem, st);
+        case 16: return launch_bwd_one<LT, 16, false>(tmap, p, grid, smem, st);
+        default: return launch_bwd_one<LT, 8, false>(tmap, p, grid, smem, st);
     }
 }
 
@@ -271,7 +303,8 @@ int launch_backward(const BwdArgs& a) {
     if (((uintptr_t)a.logits % esz) || ((uintptr_t)a.grad_logits % esz) ||
         (a.ydtype == SF_I64 && ((uintptr_t)a.labels % 8))) return SF_ERR_ALIGN;
 
-    if (!env_no_fast()) {
+    if (a.coef_a && (!a.coef_b || !a.dice_tb)) return SF_ERR_ARG;
+    if (!env_no_fast() && !a.coef_a) {                             // the dice variant exists in the generic kernel only
         int rc = launch_backward_direct(a);                        // logits already at label resolution (sf_direct.cu)
         if (rc != -1000) return rc;
         rc = launch_backward_fast(a);                              // integer-scale specialisation (sf_backward_fast.cu)
@@ -280,6 +313,7 @@ int launch_backward(const BwdArgs& a) {
     BwdParams p{};
     p.logits = a.logits; p.labels = a.labels; p.class_w = a.class_w; p.loss_px = a.loss_px; p.lse_px = a.lse_px;
     p.grad_out = a.grad_out; p.ws = reinterpret_cast<const Workspace*>(a.ws); p.grad = a.grad_logits;
+    p.coef_a = a.coef_a; p.coef_b = a.coef_b; p.dice_tb = a.dice_tb;
     p.ay = Axis{a.h, a.H, (float)a.h / (float)a.H, a.h == a.H};
     p.ax = Axis{a.w, a.W, (float)a.w / (float)a.W, a.w == a.W};
     p.B = a.B; p.C = a.C; p.ignore = a.ignore; p.label_u8 = a.ydtype == SF_U8;

@@ -17,80 +17,9 @@
 //     (__match_any_sync), flushed once per CTA with 64-bit global atomics.
 //   * loss sums are kept per thread in double, reduced per CTA in a fixed order and written to the
 //     workspace (no atomics -> bitwise reproducible loss).
-#include "sf_common.cuh"
-#include "sf_launch.h"
+#include "sf_fwd_generic.cuh"
 
 namespace sf {
-
-constexpr int kFwdTW = 64;                 // output columns per tile (= threads in x)
-constexpr int kFwdNGY = 4;                 // row groups per tile     (= threads in y)
-constexpr int kFwdThreads = kFwdTW * kFwdNGY;
-constexpr int kFwdG = 4;                   // rows of a group handled per pass (register state per thread)
-constexpr int kFwdStages = 3;
-constexpr int kFwdBH = kFwdNGY + 1;        // source rows per box
-
-struct FwdParams {
-    const void* logits;
-    const void* labels;
-    const float* class_w;
-    float* loss_px;
-    float* lse_px;
-    unsigned long long* hist;
-    Workspace* ws;
-    Axis ay, ax;
-    int B, C, ignore, label_u8;
-    float thresh;
-    int tiles_x, tiles_y, total_tiles;
-    int n_chunks, n_passes, box_w;
-    int use_tma;
-    int xalign;                            // box x-origin granularity in elements: TMA needs 16-byte aligned inner coordinates
-    int stage_bytes;                       // bytes of one smem stage (128-aligned)
-    int hist_bytes;                        // bytes reserved for the smem histogram (16-aligned)
-};
-
-struct ItemCoord { int b, ua, Xa, pass, chunk; };
-
-__host__ __device__ __forceinline__ int floor_al(int x, int a) { return x & ~(a - 1); }   // a is a power of two
-
-template <int NCH>
-__device__ __forceinline__ ItemCoord decode_item(const FwdParams& p, int n) {
-    const int ipt = p.n_passes * p.n_chunks;
-    const int tile = blockIdx.x + (n / ipt) * gridDim.x;
-    const int rem = n % ipt;
-    ItemCoord c;
-    c.pass = rem / p.n_chunks;
-    c.chunk = rem % p.n_chunks;
-    const int per_img = p.tiles_x * p.tiles_y;
-    c.b = tile / per_img;
-    const int r = tile % per_img;
-    c.ua = (p.ay.ident ? 0 : -1) + (r / p.tiles_x) * kFwdNGY;
-    c.Xa = (r % p.tiles_x) * kFwdTW;
-    return c;
-}
-
-template <typename LT, int NCH>
-__device__ __forceinline__ void issue_tma(const FwdParams& p, const CUtensorMap* tmap, const ItemCoord& c,
-                                          unsigned char* stage, uint64_t* bar) {
-    const int jA = floor_al(src_i0(p.ax, c.Xa), p.xalign);
-    mbar_expect_tx(bar, (uint32_t)(NCH * kFwdBH * p.box_w * (int)sizeof(LT)));
-    tma_load_3d(stage, tmap, bar, jA, c.ua, c.b * p.C + c.chunk * NCH);
-}
-
-// Fallback loader for shapes TMA cannot describe (row pitch not a multiple of 16 bytes).
-template <typename LT, int NCH>
-__device__ __forceinline__ void load_plain(const FwdParams& p, const ItemCoord& c, LT* stage) {
-    const int jA = floor_al(src_i0(p.ax, c.Xa), p.xalign);
-    const LT* src = reinterpret_cast<const LT*>(p.logits);
-    const int n = NCH * kFwdBH * p.box_w;
-    for (int e = threadIdx.x; e < n; e += kFwdThreads) {
-        const int col = e % p.box_w, row = (e / p.box_w) % kFwdBH, k = e / (p.box_w * kFwdBH);
-        const int ch = c.chunk * NCH + k, i = c.ua + row, j = jA + col;
-        LT v = LT(0.0f);
-        if (ch < p.C && i >= 0 && i < p.ay.in && j >= 0 && j < p.ax.in)
-            v = src[(((long long)c.b * p.C + ch) * p.ay.in + i) * p.ax.in + j];
-        stage[e] = v;
-    }
-}
 
 template <typename LT, int NCH, bool SOFTMAX>
 __global__ void __launch_bounds__(kFwdThreads, 2)
@@ -307,7 +236,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap, const FwdParams p) {
 // ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
-static int pick_nch(int C) {
+int pick_nch(int C) {
     if (C == 19) return 19;
     const int pad16 = (C + 15) / 16 * 16, pad8 = (C + 7) / 8 * 8;
     return pad8 < pad16 ? 8 : 16;
@@ -331,22 +260,9 @@ static int launch_nch(int nch, const CUtensorMap& tmap, const FwdParams& p, int 
     }
 }
 
-int launch_forward(const FwdArgs& a) {
-    if (!a.logits || !a.labels || a.B <= 0 || a.C <= 0 || a.h <= 0 || a.w <= 0 || a.H <= 0 || a.W <= 0) return SF_ERR_ARG;
-    if (a.ldtype < SF_F32 || a.ldtype > SF_F16 || a.ydtype < SF_I64 || a.ydtype > SF_U8) return SF_ERR_ARG;
-    if (a.softmax && !a.ws) return SF_ERR_ARG;
+int setup_generic_forward(const FwdArgs& a, int nch, size_t aux_bytes, FwdParams* pp, CUtensorMap* tmap_out, int* grid_out,
+                          size_t* smem_out) {
     const int esz = a.ldtype == SF_F32 ? 4 : 2;
-    if (((uintptr_t)a.logits % esz) || (a.ydtype == SF_I64 && ((uintptr_t)a.labels % 8))) return SF_ERR_ALIGN;
-    if ((long long)a.B * a.H * a.W >= (1LL << 40) || (long long)a.B * a.C >= (1LL << 31)) return SF_ERR_SHAPE;
-    if (!env_no_fast()) {
-        int rc = launch_forward_direct(a);                         // logits already at label resolution (sf_direct.cu)
-        if (rc != -1000) return rc;
-        rc = launch_forward_fast(a);                               // integer-scale specialisation (sf_forward_fast.cu)
-        if (rc != -1000) return rc;
-        rc = launch_forward_chunk(a);                              // integer scale, > 24 classes (sf_forward_chunk.cu)
-        if (rc != -1000) return rc;
-    }
-
     FwdParams p{};
     p.logits = a.logits; p.labels = a.labels; p.class_w = a.class_w;
     p.loss_px = a.loss_px; p.lse_px = a.lse_px; p.hist = a.hist; p.ws = reinterpret_cast<Workspace*>(a.ws);
@@ -355,7 +271,6 @@ int launch_forward(const FwdArgs& a) {
     p.B = a.B; p.C = a.C; p.ignore = a.ignore; p.label_u8 = a.ydtype == SF_U8;
     p.thresh = a.thresh;
 
-    const int nch = pick_nch(a.C);
     p.n_chunks = (a.C + nch - 1) / nch;
     p.tiles_x = (a.W + kFwdTW - 1) / kFwdTW;
     const int n_groups = p.ay.ident ? a.H : a.h + 1;               // u = -1 .. h-1 (or 0 .. H-1)
@@ -381,7 +296,7 @@ int launch_forward(const FwdArgs& a) {
     if (p.box_w > 256) return SF_ERR_SHAPE;
     p.stage_bytes = ((nch * kFwdBH * p.box_w * esz) + 127) & ~127;
 
-    const size_t hist_bytes = a.hist ? (((size_t)a.C * a.C * 4 + 15) & ~(size_t)15) : 16;
+    const size_t hist_bytes = aux_bytes;
     p.hist_bytes = (int)hist_bytes;
     const size_t smem = (size_t)kFwdStages * p.stage_bytes + hist_bytes + kFwdStages * 8 + 16;
     if (smem > 227 * 1024) return SF_ERR_TOO_MANY_CLASSES;
@@ -396,7 +311,37 @@ int launch_forward(const FwdArgs& a) {
         p.use_tma = 1;
     }
 
-    int grid = std::min<long long>(total, std::min(kMaxCtas, 2 * sm_count()));
+    *grid_out = (int)std::min<long long>(total, std::min(kMaxCtas, 2 * sm_count()));
+    *smem_out = smem;
+    *tmap_out = tmap;
+    *pp = p;
+    return 0;
+}
+
+int launch_forward(const FwdArgs& a) {
+    if (!a.logits || !a.labels || a.B <= 0 || a.C <= 0 || a.h <= 0 || a.w <= 0 || a.H <= 0 || a.W <= 0) return SF_ERR_ARG;
+    if (a.ldtype < SF_F32 || a.ldtype > SF_F16 || a.ydtype < SF_I64 || a.ydtype > SF_U8) return SF_ERR_ARG;
+    if (a.softmax && !a.ws) return SF_ERR_ARG;
+    const int esz = a.ldtype == SF_F32 ? 4 : 2;
+    if (((uintptr_t)a.logits % esz) || (a.ydtype == SF_I64 && ((uintptr_t)a.labels % 8))) return SF_ERR_ALIGN;
+    if ((long long)a.B * a.H * a.W >= (1LL << 40) || (long long)a.B * a.C >= (1LL << 31)) return SF_ERR_SHAPE;
+    if (!env_no_fast()) {
+        int rc = launch_forward_direct(a);                         // logits already at label resolution (sf_direct.cu)
+        if (rc != -1000) return rc;
+        rc = launch_forward_fast(a);                               // integer-scale specialisation (sf_forward_fast.cu)
+        if (rc != -1000) return rc;
+        rc = launch_forward_chunk(a);                              // integer scale, > 24 classes (sf_forward_chunk.cu)
+        if (rc != -1000) return rc;
+    }
+
+    const int nch = pick_nch(a.C);
+    const size_t hist_bytes = a.hist ? (((size_t)a.C * a.C * 4 + 15) & ~(size_t)15) : 16;
+    FwdParams p{};
+    CUtensorMap tmap{};
+    int grid = 0;
+    size_t smem = 0;
+    const int rc = setup_generic_forward(a, nch, hist_bytes, &p, &tmap, &grid, &smem);
+    if (rc != 0) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(a.stream);
     if (a.ldtype == SF_F32)
         return a.softmax ? launch_nch<float, true>(nch, tmap, p, grid, smem, st) : launch_nch<float, false>(nch, tmap, p, grid, smem, st);

@@ -34,6 +34,7 @@ struct BwdArgs {
     const float* loss_px; const float* lse_px;
     const float* grad_out;
     const void* ws;
+    const float* coef_a; const float* coef_b; const float* dice_tb;   // non-null: CE + dice gradient (sf_dice.cu)
     void* grad_logits;
     void* stream;
     bool force_no_tma;
@@ -41,6 +42,13 @@ struct BwdArgs {
 int launch_backward(const BwdArgs& a);
 int launch_backward_direct(const BwdArgs& a);
 int launch_backward_fast(const BwdArgs& a);   // -1000: shape not covered
+
+// dice term of engine.criterion (sf_dice.cu)
+size_t dice_ws_bytes(int B, int C);
+int launch_dice_stats(const FwdArgs& a, const float* lse_px, void* dice_ws);
+int launch_dice_finalize(int B, int C, float eps, const void* ws, void* dice_ws, float* loss_out, void* stream);
+int launch_dice_coef(const FwdArgs& a, const float* lse_px, const void* dice_ws, float* coef_a, float* coef_b);
+const float* dice_tb_table(const void* dice_ws, int B, int C);
 
 int launch_finalize(const float* loss_px, long long n_px, float thresh, void* ws, float* loss_out, void* stream);
 int launch_focal(float* loss_px, long long n_px, float alpha, float gamma, int size_average, void* ws,

@@ -178,3 +178,73 @@ def fused_focal_loss(logits, labels, alpha=1.0, gamma=0.0, size_average=True, ig
     B, C, h, w = logits.shape
     labels = prep_labels(labels, B, (h, w))
     return _FusedCE.apply(logits, labels, None, int(ignore_index), -1.0, None, (float(alpha), float(gamma), bool(size_average)))
+
+
+class _FusedCriterion(torch.autograd.Function):
+    """engine.criterion with dice=True: mean CE + multiclass dice loss.  Forward = sf_ce_forward + sf_loss_finalize +
+    sf_dice_stats + sf_dice_finalize (+ sf_dice_coef when a gradient is wanted), backward = sf_dice_backward."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, class_w, ignore, eps):
+        L = _lib.lib()
+        B, C, h, w = logits.shape
+        _, H, W = labels.shape
+        dev = logits.device
+        n_px = B * H * W
+        need_grad = ctx.needs_input_grad[0]
+        ws_bytes = L.sf_workspace_bytes()
+        dws_bytes = L.sf_dice_workspace_bytes(B, C)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        dws = torch.empty(dws_bytes, dtype=torch.uint8, device=dev)
+        lse_px = torch.empty(n_px, dtype=torch.float32, device=dev)
+        out = torch.empty((), dtype=torch.float32, device=dev)
+        geo = (B, C, h, w, H, W, int(ignore))
+        coef = None
+        with torch.cuda.device(dev):
+            st = _stream(dev)
+            lc, yc = _LOGIT_CODE[logits.dtype], _LABEL_CODE[labels.dtype]
+            rc = L.sf_ce_forward(_ptr(logits), lc, _ptr(labels), yc, *geo, _ptr(class_w), -1.0,
+                                 None, _ptr(lse_px), None, _ptr(ws), ws_bytes, st)
+            _lib.check(rc, "sf_ce_forward")
+            rc = L.sf_loss_finalize(None, n_px, -1.0, _ptr(ws), ws_bytes, None, st)
+            _lib.check(rc, "sf_loss_finalize")
+            rc = L.sf_dice_stats(_ptr(logits), lc, _ptr(labels), yc, *geo, _ptr(lse_px), _ptr(dws), dws_bytes, st)
+            _lib.check(rc, "sf_dice_stats")
+            rc = L.sf_dice_finalize(B, C, float(eps), _ptr(ws), _ptr(dws), dws_bytes, _ptr(out), st)
+            _lib.check(rc, "sf_dice_finalize")
+            if need_grad:
+                coef = torch.empty((2, n_px), dtype=torch.float32, device=dev)
+                rc = L.sf_dice_coef(_ptr(logits), lc, _ptr(labels), yc, *geo, _ptr(class_w), _ptr(lse_px), _ptr(ws),
+                                    _ptr(dws), dws_bytes, _ptr(coef[0]), _ptr(coef[1]), st)
+                _lib.check(rc, "sf_dice_coef")
+        ctx.geo = geo
+        ctx.dws = dws
+        ctx.save_for_backward(logits, labels, lse_px, coef)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        logits, labels, lse_px, coef = ctx.saved_tensors
+        L = _lib.lib()
+        dev = logits.device
+        g = grad_out.detach().to(device=dev, dtype=torch.float32).contiguous()
+        grad = torch.empty_like(logits)
+        with torch.cuda.device(dev):
+            rc = L.sf_dice_backward(_ptr(logits), _LOGIT_CODE[logits.dtype], _ptr(labels), _LABEL_CODE[labels.dtype],
+                                    *ctx.geo, _ptr(lse_px), _ptr(coef[0]), _ptr(coef[1]), _ptr(ctx.dws), ctx.dws.numel(),
+                                    _ptr(g), _ptr(grad), _stream(dev))
+        _lib.check(rc, "sf_dice_backward")
+        return grad, None, None, None, None
+
+
+def fused_criterion(logits, labels, weight=None, dice=True, ignore_index=255, epsilon=1e-6):
+    """engine.criterion (engine.py:10-15): F.cross_entropy(ignore_index, weight) + dice_loss(multiclass) on logits that
+    may be lower-resolution than the labels."""
+    if not dice:
+        return fused_cross_entropy(logits, labels, weight, ignore_index)
+    if 0 <= int(ignore_index) <= 1:
+        raise ValueError("ignore_index 0 or 1 collides with the one-hot values build_target compares against")
+    logits = prep_logits(logits)
+    B, C, h, w = logits.shape
+    labels = prep_labels(labels, B, (h, w))
+    return _FusedCriterion.apply(logits, labels, _class_w(weight, C, logits.device), int(ignore_index), float(epsilon))

@@ -19,11 +19,21 @@ def pytest_configure(config):
 def golden_names():
     return sorted(os.path.splitext(os.path.basename(p))[0]
                   for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                  if "hist_f32" not in p and not os.path.basename(p).startswith("focal_"))
+                  if "hist_f32" not in p and not os.path.basename(p).startswith(("focal_", "crit_")))
 
 
 def focal_names():
     return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "focal_*.npz")))
+
+
+def criterion_names():
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "crit_*.npz")))
+
+
+def load_criterion(name):
+    d = load_focal(name)
+    d["class_w"] = d["class_w"] if d["class_w"].size else None
+    return d
 
 
 def load_focal(name):

@@ -130,6 +130,39 @@ def focal_case(name, seed, B, C, hw, HW, kind, alpha, gamma, size_average, dtype
     print(f"{name:28s} focal={val.item():.6f}")
 
 
+def criterion_case(name, seed, B, C, hw, HW, kind, weighted=False, dice=True, dtype=torch.float32, dead_image=False):
+    """engine.criterion (engine.py:10-15): CE + multiclass dice loss through the upsample."""
+    from engine import criterion                                                    # the reference's own function
+    g = torch.Generator().manual_seed(seed)
+    (h, w), (H, W) = hw, HW
+    labels = make_labels(g, B, C, H, W)
+    if dead_image:
+        labels[0].fill_(255)                                                        # empty roi -> sets_sum == 0 branch
+    low = make_logits(g, kind, B, C, h, w, labels).to(dtype)
+    cw = torch.rand(C, generator=torch.Generator().manual_seed(7)) + 0.5 if weighted else None
+    lowg = low.clone().requires_grad_(True)
+    up = F.interpolate(lowg, size=(H, W), mode="bilinear", align_corners=False).float()
+    val = criterion(up, labels, cw, num_classes=C, dice=dice, ignore_index=255)
+    val.backward()
+    with torch.no_grad():
+        ce = F.cross_entropy(up, labels, ignore_index=255, weight=cw)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), logits=bits(low), logits_dtype=str(dtype).replace("torch.", ""),
+                        labels=labels.numpy(), size=np.array([H, W]), dice=np.int32(dice),
+                        class_w=(cw.numpy() if weighted else np.zeros(0, np.float32)),
+                        loss=np.float32(val.item()), ce=np.float32(ce.item()), grad=lowg.grad.float().numpy())
+    print(f"{name:28s} criterion={val.item():.6f} ce={ce.item():.6f}")
+
+
+def criterion_cases():
+    criterion_case("crit_city_early", 61, 2, 19, (16, 32), (64, 128), "early")
+    criterion_case("crit_city_late", 62, 2, 19, (16, 32), (64, 128), "late")
+    criterion_case("crit_binary_weighted", 63, 2, 2, (16, 32), (64, 128), "early", weighted=True)
+    criterion_case("crit_ade_nonint", 64, 1, 150, (18, 23), (64, 80), "late")
+    criterion_case("crit_voc_bf16", 65, 1, 21, (30, 41), (100, 135), "early", dtype=torch.bfloat16)
+    criterion_case("crit_dead_image", 66, 2, 19, (16, 32), (64, 128), "early", dead_image=True)
+    criterion_case("crit_nodice_weighted", 67, 1, 19, (16, 32), (64, 128), "early", weighted=True, dice=False)
+
+
 def hist_f32_case():
     """Metrics.hist float32 accumulation past 2**24 and compute_* on a big matrix."""
     g = torch.Generator().manual_seed(99)
@@ -155,6 +188,9 @@ def hist_f32_case():
 
 
 if __name__ == "__main__":
+    if sys.argv[1:] == ["crit"]:
+        criterion_cases()
+        sys.exit(0)
     run_case("city_early_ohem", 1234, 2, 19, (16, 32), (64, 128), "early")
     run_case("city_late_ohem", 1235, 2, 19, (16, 32), (64, 128), "late", flip_p=0.01)
     run_case("city_early_ce_u8", 1236, 1, 19, (16, 32), (64, 128), "early", ldt=torch.uint8, loss="ce")
@@ -179,3 +215,4 @@ if __name__ == "__main__":
     focal_case("focal_g2_mean", 51, 2, 19, (16, 32), (64, 128), "early", 0.25, 2.0, True)
     focal_case("focal_default", 52, 1, 19, (16, 32), (64, 128), "late", 1, 0, True)
     focal_case("focal_g15_sum_bf16", 53, 1, 21, (30, 41), (100, 135), "early", 0.5, 1.5, False, torch.bfloat16)
+    criterion_cases()

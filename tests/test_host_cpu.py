@@ -20,7 +20,8 @@ def test_library_exports_every_declared_symbol():
     L = _lib.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.sf_version() == 100
+    assert L.sf_version() == 101
+    assert L.sf_dice_workspace_bytes(8, 19) >= 64 + 8 * 19 * 32 and L.sf_dice_workspace_bytes(0, 19) == 0
     assert L.sf_workspace_bytes() > 64
     assert L.sf_strerror(0) == b"ok" and b"argument" in L.sf_strerror(-1)
 
@@ -33,6 +34,10 @@ def test_no_cpu_fallback_and_input_validation():
         sf.OhemCrossEntropy()(x, y)
     with pytest.raises(SegFactoryError):
         sf.CrossEntropy()(x, y)
+    with pytest.raises(SegFactoryError):
+        sf.criterion(x, y, None, num_classes=19, dice=True, ignore_index=255)
+    with pytest.raises(ValueError):
+        sf.criterion(x, y, None, num_classes=2, dice=True, ignore_index=255)
     with pytest.raises(SegFactoryError):
         sf.Metrics(19, 255, "cpu").update(x, y)
     with pytest.raises(SegFactoryError):

@@ -5,7 +5,7 @@ import hashlib
 import numpy as np
 import pytest
 
-from conftest import focal_names, golden_names, load_focal, load_golden
+from conftest import criterion_names, focal_names, golden_names, load_criterion, load_focal, load_golden
 
 DT = {"float32": 0, "bfloat16": 1, "float16": 2}
 
@@ -87,3 +87,14 @@ def test_focal_loss_and_gradient(oracle, name):
     assert abs(loss - float(g["loss"])) <= 2e-6 * abs(float(g["loss"]))
     tol = 1e-5 if g["logits_dtype"] == "float32" else 1e-2
     assert np.abs(grad - g["grad"]).max() <= tol * np.abs(g["grad"]).max()
+
+
+@pytest.mark.parametrize("name", criterion_names())
+def test_criterion_loss_and_gradient(oracle, name):
+    """engine.criterion = CE + multiclass dice loss against the reference's own function."""
+    g = load_criterion(name)
+    dt = DT[g["logits_dtype"]]
+    loss, grad, info = oracle.criterion_loss_and_grad(g["logits"], g["labels"], g["class_w"], bool(g["dice"]), 255, dt)
+    assert abs(loss - float(g["loss"])) <= 1e-5 * abs(float(g["loss"])), (loss, float(g["loss"]))
+    tol = 1e-5 if g["logits_dtype"] == "float32" else 1e-2
+    assert np.abs(grad - g["grad"]).max() <= tol * np.abs(g["grad"]).max(), (np.abs(grad - g["grad"]).max(), np.abs(g["grad"]).max())
