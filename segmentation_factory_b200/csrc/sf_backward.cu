@@ -304,8 +304,8 @@ int launch_backward(const BwdArgs& a) {
         (a.ydtype == SF_I64 && ((uintptr_t)a.labels % 8))) return SF_ERR_ALIGN;
 
     if (a.coef_a && (!a.coef_b || !a.dice_tb)) return SF_ERR_ARG;
-    if (!env_no_fast() && !a.coef_a) {                             // the dice variant exists in the generic kernel only
-        int rc = launch_backward_direct(a);                        // logits already at label resolution (sf_direct.cu)
+    if (!env_no_fast()) {
+        int rc = a.coef_a ? -1000 : launch_backward_direct(a);     // logits already at label resolution (sf_direct.cu; no dice variant)
         if (rc != -1000) return rc;
         rc = launch_backward_fast(a);                              // integer-scale specialisation (sf_backward_fast.cu)
         if (rc != -1000) return rc;

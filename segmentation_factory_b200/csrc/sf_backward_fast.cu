@@ -34,6 +34,9 @@ struct BfParams {
     const float* lse_px;
     const float* grad_out;
     const Workspace* ws;
+    const float* coef_a;                        // DICE (engine.criterion): per-pixel A and Bc from sf_dice.cu,
+    const float* coef_b;                        //   d/dz_k = p_k (A + tb[b][k]) - [k == y] Bc
+    const float* dice_tb;                       // [B][Ctot]
     void* grad;
     int B, h, w, H, W, ignore, label_u8;
     int tiles_x, tiles_y;
@@ -74,7 +77,7 @@ __device__ __forceinline__ void onehot_sub2(int y, float2 (&a0)[C / 2 > 0 ? C / 
 // C = channels handled by one CTA.  CHUNK = false: C is the class count.  CHUNK = true: the classes are split into
 // ceil(Ctot / C) chunks, one CTA per (tile, chunk) -- chunks are independent in the backward because the softmax
 // denominator arrives as lse_px; label/lse/loss are re-read per chunk (L2 hits: the chunk index varies fastest).
-template <typename LT, int C, int S, bool CHUNK>
+template <typename LT, int C, int S, bool CHUNK, bool DICE>
 __global__ void __launch_bounds__(kBfThreads, 4)
 bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
     static_assert(C <= 24, "onehot_sub2 covers 24 classes");
@@ -104,6 +107,11 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
     const int ja = txi * G::TBW, jb = min(ja + G::TBW, p.w);
     const int nown = jb - ja;
     const int jO = (ja - 1) & ~(G::XAL - 1);                        // box x-origin: 16-byte aligned, -XAL for the first tile
+    __shared__ float2 kb_s[DICE ? 12 : 1];                          // DICE: tb[b][c0 + 2q], tb[b][c0 + 2q + 1] (0 past the classes)
+    if (DICE && tid < 24) {
+        const float v = tid < nvalid ? __ldg(p.dice_tb + (long long)b * Ct + c0 + tid) : 0.f;
+        reinterpret_cast<float*>(kb_s)[tid] = v;
+    }
     for (int k = tid; k < (CHUNK ? 256 : 32); k += kBfThreads) cw_s[k] = (p.class_w && k < Ct) ? __ldg(p.class_w + k) : 1.0f;
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -137,11 +145,11 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
     }
     LT* gbase = reinterpret_cast<LT*>(p.grad) + (((long long)b * Ct + c0 + kq) * p.h) * p.w + ja + jl;
 
-    const sf_loss_state* stp = &p.ws->state;
-    const int branch = stp->branch;
-    const float kth = stp->kth, tie = stp->tie_share;
+    const sf_loss_state* stp = &p.ws->state;                        // DICE: never dereferenced (per-pixel weights instead)
+    const int branch = DICE ? 3 : stp->branch;                      // DICE reads its per-pixel weight like focal does
+    const float kth = DICE ? 0.f : stp->kth, tie = DICE ? 0.f : stp->tie_share;
     const bool is_focal = branch == 3;
-    const float gscale = (p.grad_out ? __ldg(p.grad_out) : 1.0f) * stp->inv_denom;
+    const float gscale = (p.grad_out ? __ldg(p.grad_out) : 1.0f) * (DICE ? 1.0f : stp->inv_denom);
     const float2 l2e2 = splat(kLog2e);
 
     // ---- row walk state ----
@@ -149,12 +157,13 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
     const int Yb = ib >= p.h ? p.H : TP::first(ib);                // exclusive
     // Prefetched inputs of the next row (label as two 32-bit halves), fetched through running pointers so the
     // row loop carries no 64-bit multiplies; `live` counts the rows this column still has to consume.
-    int nlo = -1, nhi = -1; float nlse = 0.f, nloss = 0.f;
+    int nlo = -1, nhi = -1; float nlse = 0.f, nloss = 0.f, ncb = 0.f;
     const bool has_loss = branch != 0;
     const long long px0 = ((long long)b * p.H + Ya) * p.W + (colok ? X : 0);
     const char* lab_p = reinterpret_cast<const char*>(p.labels) + px0 * (p.label_u8 ? 1 : 8);
     const float* lse_p = p.lse_px + px0;
-    const float* loss_p = (has_loss ? p.loss_px : p.lse_px) + px0;
+    const float* loss_p = (DICE ? p.coef_a : has_loss ? p.loss_px : p.lse_px) + px0;
+    const float* cb_p = (DICE ? p.coef_b : p.lse_px) + px0;
     const long long lab_step = (long long)p.W * (p.label_u8 ? 1 : 8);
     int to_fetch = colok ? Yb - Ya : 0;
     int live = to_fetch;
@@ -164,8 +173,10 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
             else { const int2 t = __ldg(reinterpret_cast<const int2*>(lab_p)); nlo = t.x; nhi = t.y; }
             nlse = __ldg(lse_p);
             if (has_loss) nloss = __ldg(loss_p);
+            if (DICE) ncb = __ldg(cb_p);
         }
         lab_p += lab_step; lse_p += p.W; loss_p += p.W; --to_fetch;
+        if (DICE) cb_p += p.W;
     };
     prefetch();
     const int ign = p.ignore;
@@ -235,7 +246,7 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
         const float lh1_step = u < 0 ? 0.0f : inv_s;
         #pragma unroll 1
         for (int r = 0; r < cnt; ++r, lh1 += lh1_step) {
-            const int lo = nlo, hi = nhi; const float lse = nlse, loss = nloss;
+            const int lo = nlo, hi = nhi; const float lse = nlse, loss = nloss, cbv = ncb;
             const bool alive = live > 0;
             --live;
             prefetch();
@@ -245,14 +256,18 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
             if (has_loss) keep = is_focal ? loss : (loss > kth ? 1.f : (loss == kth ? tie : 0.f));   // focal: loss_px holds d focal / d ce
             const float wy = cw_s[valid ? lo : 0];
             const float coef = (valid && keep != 0.f) ? keep * wy * gscale : 0.f;     // never 0 * inf
-            if (__any_sync(0xffffffffu, coef != 0.f)) {
-                if (coef != 0.f) {
+            const bool on = DICE ? valid : coef != 0.f;
+            if (__any_sync(0xffffffffu, on)) {
+                if (on) {
                     const float lh0 = 1.0f - lh1;
                     const float lse2 = __fmul_rn(lse, kLog2e);
                     const float corr = __fmaf_rn(lse, kLog2e, -lse2);        // exact residual of rn(lse*log2e)
-                    const float cf = coef * __fmaf_rn(-corr, kLn2, 1.0f);    // 2^-corr to first order
+                    const float pf = __fmaf_rn(-corr, kLn2, 1.0f);           // 2^-corr to first order
+                    const float cf = coef * pf;
                     const float aw0 = merge ? 1.0f : lh0, aw1 = merge ? 0.0f : lh1;   // clamped last row: l0 + l1 = 1
-                    const float v0 = cf * aw0, v1 = cf * aw1, o0 = coef * aw0, o1 = coef * aw1;
+                    const float osub = DICE ? cbv * gscale : coef;
+                    const float v0 = cf * aw0, v1 = cf * aw1, o0 = osub * aw0, o1 = osub * aw1;
+                    const float u0 = gscale * pf * aw0, u1 = gscale * pf * aw1;       // DICE: weight of tb_k
                     const float2 lh0_2 = splat(lh0), lh1_2 = splat(lh1), nl2 = splat(-lse2);
                     const float2 v0_2 = splat(v0), v1_2 = splat(v1);
                     #pragma unroll
@@ -260,14 +275,21 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
                         const float2 z = rnd2<LT>(lerp2_pinned(top[q], lh0_2, bot[q], lh1_2));
                         const float2 e = __ffma2_rn(z, l2e2, nl2);
                         const float2 pc = make_float2(ex2_approx(e.x), ex2_approx(e.y));
-                        at[q] = __ffma2_rn(pc, v0_2, at[q]);
-                        ab[q] = __ffma2_rn(pc, v1_2, ab[q]);
+                        if (DICE) {
+                            const float2 kb = kb_s[q];
+                            at[q] = __ffma2_rn(pc, __ffma2_rn(kb, splat(u0), v0_2), at[q]);
+                            ab[q] = __ffma2_rn(pc, __ffma2_rn(kb, splat(u1), v1_2), ab[q]);
+                        } else {
+                            at[q] = __ffma2_rn(pc, v0_2, at[q]);
+                            ab[q] = __ffma2_rn(pc, v1_2, ab[q]);
+                        }
                     }
                     if (G::ODD) {
                         const float z = Logit<LT>::rnd(lerp_pinned(topl, lh0, botl, lh1));
                         const float pc = ex2_approx(__fmaf_rn(z, kLog2e, -lse2));
-                        atl = fmaf(pc, v0, atl);
-                        abl = fmaf(pc, v1, abl);
+                        const float kbl = DICE ? reinterpret_cast<const float*>(kb_s)[C - 1] : 0.f;
+                        atl = fmaf(pc, DICE ? fmaf(kbl, u0, v0) : v0, atl);
+                        abl = fmaf(pc, DICE ? fmaf(kbl, u1, v1) : v1, abl);
                     }
                     const int yk = ((unsigned)(lo - c0) < (unsigned)nvalid) ? lo - c0 : -1;   // label inside this CTA's classes?
                     if (yk != run_y) {
@@ -312,14 +334,15 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
 // ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
-template <typename LT, int C, int S, bool CHUNK>
-static int bf_launch(const BwdArgs& a) {
+template <typename LT, int C, int S, bool CHUNK, bool DICE>
+static int bf_launch_d(const BwdArgs& a) {
     using G = BfGeom<LT, C, S>;
     if (a.w < G::BW || a.h < kBfBH) return -1000;                   // TMA box must fit inside the tensor
     if (CHUNK && a.C > 256) return -1000;
     BfParams p{};
     p.labels = a.labels; p.class_w = a.class_w; p.loss_px = a.loss_px; p.lse_px = a.lse_px; p.grad_out = a.grad_out;
     p.ws = reinterpret_cast<const Workspace*>(a.ws); p.grad = a.grad_logits;
+    p.coef_a = a.coef_a; p.coef_b = a.coef_b; p.dice_tb = a.dice_tb;
     p.B = a.B; p.h = a.h; p.w = a.w; p.H = a.H; p.W = a.W; p.ignore = a.ignore; p.label_u8 = a.ydtype == SF_U8;
     p.tiles_x = (a.w + G::TBW - 1) / G::TBW;
     p.tiles_y = (a.h + kBfTH - 1) / kBfTH;
@@ -331,11 +354,16 @@ static int bf_launch(const BwdArgs& a) {
     if (rc != 0) return rc;
     size_t smem = (size_t)G::SRC_BYTES + (size_t)2 * C * kBfThreads * 4 + 16;
     if (const char* pad = std::getenv("SF_DEBUG_SMEM_PAD_KB")) smem += (size_t)atoi(pad) * 1024;   // experiment knob (occupancy sensitivity)
-    auto k = bwd_fast_kernel<LT, C, S, CHUNK>;
+    auto k = bwd_fast_kernel<LT, C, S, CHUNK, DICE>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     k<<<(int)grid, kBfThreads, smem, reinterpret_cast<cudaStream_t>(a.stream)>>>(tmap, p);
     return (int)cudaGetLastError();
+}
+
+template <typename LT, int C, int S, bool CHUNK>
+static int bf_launch(const BwdArgs& a) {
+    return a.coef_a ? bf_launch_d<LT, C, S, CHUNK, true>(a) : bf_launch_d<LT, C, S, CHUNK, false>(a);
 }
 
 template <typename LT, int C, bool CHUNK>

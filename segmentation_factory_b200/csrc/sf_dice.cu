@@ -24,16 +24,7 @@ constexpr float kFixS = 1099511627776.f;          // 2^40: sum p_c
 constexpr float kFixI = 67108864.f;               // 2^26: p_y of one pixel
 constexpr int   kDiceHeaderBytes = 64;
 
-struct DiceParams {
-    const float* lse_in;                           // [B*H*W] from sf_ce_forward
-    unsigned long long* stats;                     // [B][C][3]  STATS: accumulated into
-    const float* ta;                               // [B][C]     COEF
-    const float* tb;                               // [B][C]     COEF
-    float* coef_a;                                 // [B*H*W]    COEF
-    float* coef_b;
-};
-
-enum { DICE_STATS = 0, DICE_COEF = 1 };
+using DiceParams = DiceArgs;
 
 template <typename LT, int NCH, int MODE>
 __global__ void __launch_bounds__(kFwdThreads, 2)
@@ -283,6 +274,12 @@ static int launch_dice_walk(const FwdArgs& a, const DiceParams& d) {
     const int esz = a.ldtype == SF_F32 ? 4 : 2;
     if (((uintptr_t)a.logits % esz) || (a.ydtype == SF_I64 && ((uintptr_t)a.labels % 8))) return SF_ERR_ALIGN;
     if ((long long)a.H * a.W > (1LL << 23)) return SF_ERR_SHAPE;    // 2^40 fixed point of sum p_c must fit 64 bits
+    if (!env_no_fast()) {
+        FwdArgs f = a;
+        f.dice_mode = MODE; f.dice = d;
+        const int rc = launch_forward_fast(f);                     // integer-scale specialisation (sf_forward_fast.cu)
+        if (rc != -1000) return rc;
+    }
     const int nch = pick_nch(a.C);
     const size_t aux = MODE == DICE_STATS ? (((size_t)3 * a.C * 8 + 15) & ~(size_t)15) : 16;
     FwdParams p{};

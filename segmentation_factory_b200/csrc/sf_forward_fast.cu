@@ -31,7 +31,10 @@ struct FfParams {
     int B, h, w, H, W, ignore, label_u8;
     float thresh;
     int tiles_x, tiles_y, total_tiles;
+    DiceArgs dice;                                                  // MODE >= 2 (sf_dice.cu)
 };
+
+enum { FF_ARGMAX = 0, FF_SOFTMAX = 1, FF_DICE_STATS = 2, FF_DICE_COEF = 3 };
 
 template <typename LT, int C, int S>
 struct FfGeom {
@@ -46,12 +49,17 @@ struct FfGeom {
     static constexpr bool ODD = (C & 1) != 0;
 };
 
-template <typename LT, int C, int S, bool SOFTMAX>
+// MODE: FF_ARGMAX / FF_SOFTMAX are the forward proper; FF_DICE_STATS / FF_DICE_COEF are the two dice walks of
+// sf_dice.cu (same tiles, staging and strip walk, different per-pixel body: softmax from the stored lse, no argmax).
+template <typename LT, int C, int S, int MODE>
 __global__ void __launch_bounds__(kFfThreads, 2)
 fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
     using G = FfGeom<LT, C, S>;
     using TP = ScaleTap<S>;
     constexpr int NP = G::NP;
+    constexpr bool SOFTMAX = MODE == FF_SOFTMAX;
+    constexpr bool DSTAT = MODE == FF_DICE_STATS, DCOEF = MODE == FF_DICE_COEF, DICE = DSTAT || DCOEF;
+    constexpr int CP = C + (C & 1);                                 // even pitch of the per-image dice tables (LDS.64 pairs)
     extern __shared__ __align__(128) unsigned char smem[];
     int* hist_s = reinterpret_cast<int*>(smem + kFfStages * G::STAGE_BYTES);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + kFfStages * G::STAGE_BYTES + round_up(C * C * 4, 16));
@@ -61,10 +69,20 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
     const int tid = threadIdx.x;
     const int tx = tid % kFfTW, sy = tid / kFfTW;
     if (tid < 32) cw_s[tid] = (p.class_w && tid < C) ? __ldg(p.class_w + tid) : 1.0f;
-    const bool want_hist = p.hist != nullptr;
+    const bool want_hist = !DICE && p.hist != nullptr;
+    unsigned long long* bins = reinterpret_cast<unsigned long long*>(hist_s);          // DSTAT: [3][C] in the histogram area
+    float* tab_s = reinterpret_cast<float*>(full + kFfStages);                          // DCOEF: ta[B][CP], tb[B][CP]
+    const int lane = tid & 31;
 
     if (want_hist)
         for (int k = tid; k < C * C; k += kFfThreads) hist_s[k] = 0;
+    if (DSTAT)
+        for (int k = tid; k < 3 * C; k += kFfThreads) bins[k] = 0ull;
+    if (DCOEF)
+        for (int k = tid; k < 2 * p.B * CP; k += kFfThreads) {
+            const int which = k / (p.B * CP), r = k % (p.B * CP), bb = r / CP, cc = r % CP;
+            tab_s[k] = cc < C ? __ldg((which ? p.dice.tb : p.dice.ta) + bb * C + cc) : 0.f;
+        }
     if (tid == 0) {
         tma_prefetch_desc(&tmap);
         for (int s = 0; s < kFfStages; ++s) mbar_init(&full[s], 1);
@@ -92,11 +110,56 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
     unsigned int cnt_valid = 0, cnt_hard = 0;
     const float2 l2e2 = splat(kLog2e);
 
+    // ---- dice state: sum p_k of this thread's roi pixels (DSTAT), flushed as integers so the result is order-free ----
+    float2 accp[(DSTAT && NP > 0) ? NP : 1];
+    float accpl = 0.f;
+    #pragma unroll
+    for (int q = 0; q < ((DSTAT && NP > 0) ? NP : 1); ++q) accp[q] = make_float2(0.f, 0.f);
+    int cur_b = -1, since_flush = 0;
+    const float inv_denom = (DCOEF && p.ws) ? p.ws->state.inv_denom : 0.f;
+    auto redux3 = [&](float v) -> unsigned long long {               // warp sum of v (<= 2^7) in 2^40 fixed point
+        const unsigned long long f = __float2ull_rn(v * 1099511627776.f);
+        const unsigned a = __reduce_add_sync(0xffffffffu, (unsigned)(f & 0xFFFFFull));
+        const unsigned bq = __reduce_add_sync(0xffffffffu, (unsigned)((f >> 20) & 0xFFFFFull));
+        const unsigned cq = __reduce_add_sync(0xffffffffu, (unsigned)(f >> 40));
+        return ((unsigned long long)cq << 40) + ((unsigned long long)bq << 20) + a;
+    };
+    auto flush_acc = [&]() {                                         // registers -> shared bins (all lanes of every warp)
+        #pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            const unsigned long long sx = redux3(accp[q].x), sy2 = redux3(accp[q].y);
+            if (lane == 0) { if (sx) atomicAdd(&bins[2 * q], sx); if (sy2) atomicAdd(&bins[2 * q + 1], sy2); }
+            accp[q] = make_float2(0.f, 0.f);
+        }
+        if (G::ODD) {
+            const unsigned long long sl = redux3(accpl);
+            if (lane == 0 && sl) atomicAdd(&bins[C - 1], sl);
+            accpl = 0.f;
+        }
+        since_flush = 0;
+    };
+    auto flush_bins = [&](int b) {                                   // CTA-uniform: image b's bins -> global
+        __syncthreads();
+        for (int k = tid; k < 3 * C; k += kFfThreads) {
+            const unsigned long long v = bins[k];
+            if (v) atomicAdd(p.dice.stats + ((long long)b * C + k % C) * 3 + k / C, v);
+            bins[k] = 0ull;
+        }
+        __syncthreads();
+    };
+
     for (int n = 0; n < n_tiles; ++n) {
         const int tile = blockIdx.x + n * gridDim.x;
         const int b = tile / per_img, rr = tile % per_img;
         const int ua = -1 + (rr / p.tiles_x) * G::NGT;
         const int Xa = (rr % p.tiles_x) * kFfTW;
+        if (DSTAT) {
+            if (b != cur_b || since_flush >= 8) {                    // keep the fp32 partials short (<= 128 pixels)
+                flush_acc();
+                if (b != cur_b) { if (cur_b >= 0) flush_bins(cur_b); cur_b = b; }
+            }
+            ++since_flush;
+        }
         const int X = Xa + tx;
         const bool colok = X < p.W;
         int j0, j1; float lw0, lw1;
@@ -111,6 +174,7 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
         // Labels travel as one byte each (valid classes < C <= 24 here, 255 = not counted), packed 8 per register
         // pair.  Raw 64-bit loads for the NEXT group are issued a whole group ahead and only decoded when needed.
         long long raw[S];
+        float lsn[DICE ? S : 1], lsc[DICE ? S : 1];                  // DICE: the stored lse travels with the labels
         auto fetch_labels = [&](int u) {
             #pragma unroll
             for (int r = 0; r < S; ++r) raw[r] = -1;
@@ -119,13 +183,17 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
                 const long long base = ((long long)b * p.H + y0) * p.W + X;
                 #pragma unroll
                 for (int r = 0; r < S; ++r)
-                    if (r < cnt) raw[r] = ld_label(p.labels, p.label_u8, base + (long long)r * p.W);
+                    if (r < cnt) {
+                        raw[r] = ld_label(p.labels, p.label_u8, base + (long long)r * p.W);
+                        if (DICE) lsn[r] = __ldg(p.dice.lse_in + base + (long long)r * p.W);
+                    }
             }
         };
         auto pack_labels = [&]() -> unsigned long long {
             unsigned long long pk = 0;
             #pragma unroll
             for (int r = 0; r < S; ++r) {
+                if (DICE) lsc[r] = lsn[r];
                 const long long y = raw[r];
                 const unsigned v = (y != p.ignore && y >= 0 && y < C) ? (unsigned)y : 255u;
                 pk |= (unsigned long long)v << (8 * r);
@@ -240,6 +308,75 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
             }
         };
 
+        // dice walks: p_k = 2^(z_k log2e - rn(lse log2e)) * pcf from the stored lse; no max / argmax / histogram
+        auto do_group_dice = [&](int u, const float2 (&top)[NP > 0 ? NP : 1], float topl,
+                                 const float2 (&bot)[NP > 0 ? NP : 1], float botl, unsigned long long labs) {
+            const int i0 = max(u, 0), i1 = min(i0 + 1, p.h - 1);
+            const int cnt = TP::count(u, p.h);
+            const int o0 = (i0 - ua) * G::BW, o1 = (i1 - ua) * G::BW;
+            const int cj0 = j0 - jO, cj1 = j1 - jO;
+            long long px = ((long long)b * p.H + TP::first(u)) * p.W + X;
+            #pragma unroll
+            for (int r = 0; r < S; ++r) {
+                if (r < cnt) {                                       // warp-uniform
+                    const float lh1 = u < 0 ? 0.0f : ((float)r + 0.5f) * (1.0f / S);
+                    const float lh0 = 1.0f - lh1;
+                    const int lab = (int)((labs >> (8 * r)) & 0xffu);
+                    const bool valid = lab != 255;                   // also false outside the image (raw = -1)
+                    const float lse = valid ? lsc[r] : 0.f;
+                    const float lse2 = __fmul_rn(lse, kLog2e);
+                    const float pcf = valid ? __fmaf_rn(-__fmaf_rn(lse, kLog2e, -lse2), kLn2, 1.0f) : 0.f;
+                    const float2 lh0_2 = splat(lh0), lh1_2 = splat(lh1), nl2 = splat(-lse2), pcf2 = splat(pcf);
+                    float2 g2 = make_float2(0.f, 0.f);
+                    if (__any_sync(0xffffffffu, valid)) {
+                        #pragma unroll
+                        for (int q = 0; q < NP; ++q) {
+                            const float2 z = rnd2<LT>(lerp2_pinned(top[q], lh0_2, bot[q], lh1_2));
+                            const float2 e = __ffma2_rn(z, l2e2, nl2);
+                            const float2 ex = make_float2(ex2_approx(e.x), ex2_approx(e.y));
+                            if (DSTAT) accp[q] = __ffma2_rn(ex, pcf2, accp[q]);
+                            else g2 = __ffma2_rn(ex, *reinterpret_cast<const float2*>(tab_s + (p.B + b) * CP + 2 * q), g2);
+                        }
+                        if (G::ODD) {
+                            const float zl = Logit<LT>::rnd(lerp_pinned(topl, lh0, botl, lh1));
+                            const float exl = ex2_approx(__fmaf_rn(zl, kLog2e, -lse2));
+                            if (DSTAT) accpl = fmaf(exl, pcf, accpl);
+                            else g2.x = fmaf(exl, tab_s[(p.B + b) * CP + C - 1], g2.x);
+                        }
+                    }
+                    float py = 0.f;
+                    if (valid) {                                     // label logit: same ops as the z entry of that channel
+                        const LT* qk = Sg + lab * G::PLANE;
+                        const float t0 = lerp_pinned(Logit<LT>::ld(qk + o0 + cj0), lw0, Logit<LT>::ld(qk + o0 + cj1), lw1);
+                        const float t1 = lerp_pinned(Logit<LT>::ld(qk + o1 + cj0), lw0, Logit<LT>::ld(qk + o1 + cj1), lw1);
+                        const float zy = Logit<LT>::rnd(lerp_pinned(t0, lh0, t1, lh1));
+                        py = ex2_approx(__fmaf_rn(zy, kLog2e, -lse2)) * pcf;
+                    }
+                    if (DSTAT) {
+                        const int key = valid ? lab : -1;
+                        const unsigned peers = __match_any_sync(0xffffffffu, key);
+                        const unsigned sum = __reduce_add_sync(peers, valid ? __float2uint_rn(py * 67108864.f) : 0u);
+                        if (valid && lane == __ffs(peers) - 1) {
+                            atomicAdd(&bins[C + lab], (unsigned long long)sum);
+                            atomicAdd(&bins[2 * C + lab], (unsigned long long)__popc(peers));
+                        }
+                    } else if (colok) {
+                        float ca = 0.f, cb = 0.f;
+                        if (valid) {
+                            cb = fmaf(tab_s[b * CP + lab], py, inv_denom * cw_s[lab]);
+                            ca = cb - (g2.x + g2.y) * pcf;
+                        }
+                        p.dice.coef_a[px + (long long)r * p.W] = ca;
+                        p.dice.coef_b[px + (long long)r * p.W] = cb;
+                    }
+                }
+            }
+        };
+        auto group = [&](int u, const float2 (&top)[NP > 0 ? NP : 1], float topl,
+                         const float2 (&bot)[NP > 0 ? NP : 1], float botl, unsigned long long labs) {
+            if (DICE) do_group_dice(u, top, topl, bot, botl, labs); else do_group(u, top, topl, bot, botl, labs);
+        };
+
         // strip walk, two groups per iteration so the bottom row of one group becomes the top row of the next
         // by swapping the roles of ta/tb (no register copies)
         int u = u_first;
@@ -251,7 +388,7 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
             if (u < 0) {                                             // rim group u = -1 shares (row 0, row 1) with u = 0
                 const unsigned long long labs = pack_labels();
                 fetch_labels(u + 1);
-                do_group(u, ta, tal, tb, tbl, labs);
+                group(u, ta, tal, tb, tbl, labs);
                 ++u;
             }
         }
@@ -259,7 +396,7 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
             {
                 const unsigned long long labs = pack_labels();
                 fetch_labels(u + 1 < u_end ? u + 1 : p.h);
-                do_group(u, ta, tal, tb, tbl, labs);
+                group(u, ta, tal, tb, tbl, labs);
                 ++u;
             }
             if (u >= u_end) break;
@@ -268,7 +405,7 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
                 hrow(i1 - ua, ta, tal);                              // ta: new bottom row, tb: top row
                 const unsigned long long labs = pack_labels();
                 fetch_labels(u + 1 < u_end ? u + 1 : p.h);
-                do_group(u, tb, tbl, ta, tal, labs);
+                group(u, tb, tbl, ta, tal, labs);
                 ++u;
             }
             if (u >= u_end) break;
@@ -283,6 +420,10 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
         if (tid == 0 && n + kFfStages < n_tiles) issue(n + kFfStages);
     }
 
+    if (DSTAT) {
+        flush_acc();
+        if (cur_b >= 0) flush_bins(cur_b);
+    }
     if (want_hist) {
         for (int k = tid; k < C * C; k += kFfThreads) {
             const int v = hist_s[k];
@@ -306,14 +447,14 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
 // ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
-template <typename LT, int C, int S, bool SOFTMAX>
+template <typename LT, int C, int S, int MODE>
 static int ff_launch(const FwdArgs& a) {
     using G = FfGeom<LT, C, S>;
     FfParams p{};
     p.labels = a.labels; p.class_w = a.class_w; p.loss_px = a.loss_px; p.lse_px = a.lse_px; p.hist = a.hist;
     p.ws = reinterpret_cast<Workspace*>(a.ws);
     p.B = a.B; p.h = a.h; p.w = a.w; p.H = a.H; p.W = a.W; p.ignore = a.ignore; p.label_u8 = a.ydtype == SF_U8;
-    p.thresh = a.thresh;
+    p.thresh = a.thresh; p.dice = a.dice;
     p.tiles_x = (a.W + kFfTW - 1) / kFfTW;
     p.tiles_y = (a.h + 1 + G::NGT - 1) / G::NGT;
     const long long total = (long long)a.B * p.tiles_x * p.tiles_y;
@@ -322,8 +463,12 @@ static int ff_launch(const FwdArgs& a) {
     CUtensorMap tmap{};
     const int rc = make_logits_tmap(&tmap, a.logits, a.ldtype, a.B * C, a.h, a.w, C, G::BH, G::BW);
     if (rc != 0) return rc;
-    const size_t smem = (size_t)kFfStages * G::STAGE_BYTES + round_up(C * C * 4, 16) + kFfStages * 8 + 16;
-    auto k = fwd_fast_kernel<LT, C, S, SOFTMAX>;
+    size_t smem = (size_t)kFfStages * G::STAGE_BYTES + round_up(C * C * 4, 16) + kFfStages * 8 + 16;
+    if (MODE == FF_DICE_COEF) {
+        if ((long long)a.B * (C + 1) > 4096) return -1000;           // per-image tables live in shared memory
+        smem += (size_t)2 * a.B * (C + (C & 1)) * 4;
+    }
+    auto k = fwd_fast_kernel<LT, C, S, MODE>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     const char* gm = std::getenv("SF_DEBUG_CTAS_PER_SM");             // experiment knob (occupancy sensitivity)
@@ -335,7 +480,9 @@ static int ff_launch(const FwdArgs& a) {
 
 template <typename LT, int C, int S>
 static int ff_mode(const FwdArgs& a) {
-    return a.softmax ? ff_launch<LT, C, S, true>(a) : ff_launch<LT, C, S, false>(a);
+    if (a.dice_mode == DICE_STATS) return ff_launch<LT, C, S, FF_DICE_STATS>(a);
+    if (a.dice_mode == DICE_COEF) return ff_launch<LT, C, S, FF_DICE_COEF>(a);
+    return a.softmax ? ff_launch<LT, C, S, FF_SOFTMAX>(a) : ff_launch<LT, C, S, FF_ARGMAX>(a);
 }
 template <typename LT, int C>
 static int ff_scale(const FwdArgs& a, int s) {

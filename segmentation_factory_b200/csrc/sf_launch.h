@@ -8,6 +8,17 @@
 
 namespace sf {
 
+// Dice walks (sf_dice.cu): the forward tile walk with a different per-pixel body.
+enum { DICE_OFF = 0, DICE_STATS = 1, DICE_COEF = 2 };
+struct DiceArgs {
+    const float* lse_in;                           // [B*H*W] from sf_ce_forward
+    unsigned long long* stats;                     // [B][C][3]  STATS: accumulated into
+    const float* ta;                               // [B][C]     COEF
+    const float* tb;                               // [B][C]     COEF
+    float* coef_a;                                 // [B*H*W]    COEF
+    float* coef_b;
+};
+
 struct FwdArgs {
     const void* logits; int ldtype;
     const void* labels; int ydtype;
@@ -20,6 +31,8 @@ struct FwdArgs {
     void* stream;
     bool softmax;          // false: argmax + histogram only (sf_eval_hist)
     bool force_no_tma;     // SF_NO_TMA=1 in the environment (debug / A-B measurement)
+    int dice_mode;         // DICE_OFF: the CE / argmax forward
+    DiceArgs dice;
 };
 int launch_forward(const FwdArgs& a);
 int launch_forward_fast(const FwdArgs& a);    // -1000: shape not covered by the integer-scale specialisation

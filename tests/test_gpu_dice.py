@@ -54,8 +54,10 @@ DICE_CASES = [
 ]
 
 
+@pytest.mark.parametrize("no_fast", ["0", "1"])
 @pytest.mark.parametrize("case", DICE_CASES, ids=[c[0] for c in DICE_CASES])
-def test_criterion_seeded_vs_oracle(sf, oracle, case):
+def test_criterion_seeded_vs_oracle(sf, oracle, case, no_fast, monkeypatch):
+    monkeypatch.setenv("SF_NO_FAST", no_fast)                      # 1: force the generic kernels on fast-path shapes
     name, seed, B, C, h, w, H, W, kind, dtype, ldt, weighted = case
     low, lab = _synth(seed, B, C, h, w, H, W, kind, dtype, ldt, blk=16)
     cw = (torch.rand(C, generator=torch.Generator().manual_seed(7)) + 0.5) if weighted else None
