@@ -164,6 +164,15 @@ int sf_dice_backward(const void* logits, int ldtype, const void* labels, int ydt
                      void* grad_logits, void* stream);
 
 /*
+ * Label ingest.  Replaces the datasets' per-sample numpy gathers -- Cityscapes.encode_target
+ * (datasets/cityscapes.py:92,130-131: id_to_train_id[np.array(target)]) and COCOStuff.encode (datasets/coco_stuff.py:66-69,
+ * 98-100: label_map[label]) -- and the int64 collate behind them: the annotation bytes are copied to the device as they are
+ * and mapped there.  out[i] = lut[raw[i]];  lut is a DEVICE table of 256 bytes;  out_dtype SF_U8 (what the kernels above
+ * read at 1 B/px) or SF_I64 (the reference's dtype).
+ */
+int sf_label_lut(const unsigned char* raw, long long n, const unsigned char* lut, void* out, int out_dtype, void* stream);
+
+/*
  * Replaces ConfusionMatrix.update(a, b) (util/utils.py:99-109) when the caller already holds the
  * flattened label / prediction index vectors (the unmodified engine.py:90 call).
  *   a [n] labels (int64 or uint8), b [n] int64 predictions in [0,C); mat[C*C] accumulated.

@@ -83,7 +83,27 @@ def torch_eager(name, B, C, h, w, H, W, kind):
     print(json.dumps({"config": name + " [torch eager, same GPU]", "ms_per_step": ms, "Gpx_s": B * H * W / ms / 1e6}), flush=True)
 
 
+def label_lut(name, B, H, W, dtype):
+    """sf_label_lut: HBM-bound streaming map, 2 B/px (uint8 out) or 9 B/px (int64 out)."""
+    lut = sf.LabelLUT(list(range(19)) + [255] * 16)
+    raws = [torch.randint(0, 35, (B, H, W), dtype=torch.uint8, device=dev) for _ in range(8)]   # 8 x 16.8 MB in, rotating
+    it = [0]
+    def step():
+        lut(raws[it[0] % 8], dtype); it[0] += 1
+    ms = timeit(step, n=200, warm=20)
+    bpp = 2 if dtype == torch.uint8 else 9
+    print(json.dumps({"config": name, "ms_per_step": ms, "Gpx_s": B * H * W / ms / 1e6, "alg_bytes_per_px": bpp,
+                      "GB_s": bpp * B * H * W / (ms * 1e-3) / 1e9,
+                      "frac_of_measured_hbm": bpp * B * H * W / (ms * 1e-3) / 1e9 / PEAK}), flush=True)
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["lut"]:
+        label_lut("label LUT 8x1024x2048 uint8 -> uint8 (incl. python + output alloc)", 8, 1024, 2048, torch.uint8)
+        label_lut("label LUT 8x1024x2048 uint8 -> int64", 8, 1024, 2048, torch.int64)
+        label_lut("label LUT 64x1024x2048 uint8 -> uint8", 64, 1024, 2048, torch.uint8)
+        label_lut("label LUT 64x1024x2048 uint8 -> int64", 64, 1024, 2048, torch.int64)
+        sys.exit(0)
     run("cfg2 cityscapes 8x19 OHEM fp32 (python API incl. allocs)", 8, 19, 256, 512, 1024, 2048, torch.float32, "ohem", 1234)
     run("cfg1 2x150x128^2->512^2 OHEM fp32", 2, 150, 128, 128, 512, 512, torch.float32, "ohem", 0)
     run("cfg3 16x150x128^2->512^2 CE fp32", 16, 150, 128, 128, 512, 512, torch.float32, "ce", 2345)

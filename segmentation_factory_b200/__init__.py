@@ -5,13 +5,15 @@ Mirrors the reference's util/ API for this path only:
     Metrics                                         (util/metrics.py)
     ConfusionMatrix                                 (util/utils.py)
     criterion (CE + dice)                           (engine.py:10-15)
+    LabelLUT (id_to_train_id / label_map on device) (datasets/cityscapes.py:92,130-131; coco_stuff.py:66-69,98-100)
 backed by hand-written sm_100a kernels in libsegfactory.so (C ABI: include/segfactory.h).
 """
+from .labels import LabelLUT
 from .losses import CrossEntropy, FocalLoss, OhemCrossEntropy, get_loss
 from .metrics import ConfusionMatrix, Metrics, fused_eval_update
 from .engine import criterion
 from .functional import eval_hist, fused_criterion, fused_cross_entropy, fused_focal_loss, hist_pairs
 
 __all__ = ["CrossEntropy", "OhemCrossEntropy", "FocalLoss", "fused_focal_loss", "get_loss", "Metrics", "ConfusionMatrix",
-           "fused_eval_update", "fused_cross_entropy", "fused_criterion", "criterion", "eval_hist", "hist_pairs"]
+           "fused_eval_update", "fused_cross_entropy", "fused_criterion", "criterion", "eval_hist", "hist_pairs", "LabelLUT"]
 __version__ = "0.1.0"

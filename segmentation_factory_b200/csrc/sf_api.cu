@@ -190,6 +190,14 @@ int sf_dice_backward(const void* logits, int ldtype, const void* labels, int ydt
     return sf::launch_backward(a);
 }
 
+int sf_label_lut(const unsigned char* raw, long long n, const unsigned char* lut, void* out, int out_dtype, void* stream) {
+    if (n < 0 || (out_dtype != SF_I64 && out_dtype != SF_U8)) return SF_ERR_ARG;
+    if (n == 0) return SF_OK;                                       // an empty tensor has no storage to point at
+    if (!raw || !lut || !out) return SF_ERR_ARG;
+    if (out_dtype == SF_I64 && ((uintptr_t)out % 8)) return SF_ERR_ALIGN;
+    return sf::launch_label_lut(raw, n, lut, out, out_dtype, stream);
+}
+
 int sf_accumulate_counts(unsigned long long* counts, float* hist_f32, long long* hist_i64, long long* mat, int n,
                          void* stream) {
     if (!counts || n <= 0) return SF_ERR_ARG;

@@ -67,6 +67,7 @@ int launch_finalize(const float* loss_px, long long n_px, float thresh, void* ws
 int launch_focal(float* loss_px, long long n_px, float alpha, float gamma, int size_average, void* ws,
                  float* loss_out, void* stream);
 int launch_accumulate_counts(unsigned long long* counts, float* hist_f32, long long* hist_i64, long long* mat, int n, void* stream);
+int launch_label_lut(const unsigned char* raw, long long n, const unsigned char* lut, void* out, int out_dtype, void* stream);
 int launch_hist_pairs(const void* a, int adtype, const long long* b, long long n, int C,
                       unsigned long long* mat, void* stream);
 

@@ -19,7 +19,7 @@ def pytest_configure(config):
 def golden_names():
     return sorted(os.path.splitext(os.path.basename(p))[0]
                   for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                  if "hist_f32" not in p and not os.path.basename(p).startswith(("focal_", "crit_")))
+                  if "hist_f32" not in p and "label_lut" not in p and not os.path.basename(p).startswith(("focal_", "crit_")))
 
 
 def focal_names():

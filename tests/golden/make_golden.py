@@ -163,6 +163,32 @@ def criterion_cases():
     criterion_case("crit_nodice_weighted", 67, 1, 19, (16, 32), (64, 128), "early", weighted=True, dice=False)
 
 
+def label_lut_case():
+    """Label ingest: the datasets' own encode functions on random raw ids."""
+    import importlib.util
+
+    def load(name, rel):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel))
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        return m
+    cs = load("ref_cityscapes", "datasets/cityscapes.py").Cityscapes
+    coco_cls = load("ref_coco_stuff", "datasets/coco_stuff.py").COCOStuff
+    g = np.random.default_rng(5)
+    raw_cs = g.integers(0, 34, (3, 67, 131), dtype=np.uint8)            # Cityscapes label ids 0..33
+    enc_cs = cs.encode_target(raw_cs)                                   # cityscapes.py:130-131
+    coco = coco_cls.__new__(coco_cls)                                   # __init__ needs the image folder; its table code:
+    coco.use_id = [i for i in range(182) if i not in coco.UNUSEID]      # coco_stuff.py:66
+    coco.label_map = np.arange(256)                                     # :67
+    for i, k in enumerate(coco.use_id):                                 # :68-69
+        coco.label_map[k] = i
+    raw_coco = g.integers(0, 256, (2, 50, 77), dtype=np.uint8)
+    enc_coco = coco.encode(raw_coco).numpy()                            # :98-100
+    np.savez_compressed(os.path.join(OUT, "label_lut.npz"), cs_table=np.asarray(cs.id_to_train_id), cs_raw=raw_cs,
+                        cs_enc=np.asarray(enc_cs), coco_table=coco.label_map, coco_raw=raw_coco, coco_enc=enc_coco)
+    print("label_lut", np.asarray(cs.id_to_train_id).shape, enc_cs.dtype, enc_coco.dtype)
+
+
 def hist_f32_case():
     """Metrics.hist float32 accumulation past 2**24 and compute_* on a big matrix."""
     g = torch.Generator().manual_seed(99)
@@ -188,6 +214,9 @@ def hist_f32_case():
 
 
 if __name__ == "__main__":
+    if sys.argv[1:] == ["lut"]:
+        label_lut_case()
+        sys.exit(0)
     if sys.argv[1:] == ["crit"]:
         criterion_cases()
         sys.exit(0)
@@ -216,3 +245,4 @@ if __name__ == "__main__":
     focal_case("focal_default", 52, 1, 19, (16, 32), (64, 128), "late", 1, 0, True)
     focal_case("focal_g15_sum_bf16", 53, 1, 21, (30, 41), (100, 135), "early", 0.5, 1.5, False, torch.bfloat16)
     criterion_cases()
+    label_lut_case()

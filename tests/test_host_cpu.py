@@ -104,3 +104,22 @@ def test_torch_restatement_matches_golden(name):
     loss, grad = tr.loss_and_grad(low, lab, g["loss_kind"], cw)
     assert loss.item() == float(g["loss"])
     assert np.array_equal(grad.float().numpy(), g["grad"])
+
+
+def test_label_lut_table_matches_reference_encoders():
+    """Host side of the label ingest: the 256-entry table reproduces Cityscapes.encode_target and
+    COCOStuff.encode on the golden raw ids; the mapping itself has no CPU path."""
+    import segmentation_factory_b200 as sf
+    from segmentation_factory_b200._lib import SegFactoryError
+    z = np.load(os.path.join(GOLDEN_DIR, "label_lut.npz"))
+    for key in ("cs", "coco"):
+        lut = sf.LabelLUT(z[key + "_table"], device="cpu")
+        assert lut.table.dtype == np.uint8 and lut.table.shape == (256,)
+        assert np.array_equal(lut.table[z[key + "_raw"]].astype(np.int64), z[key + "_enc"].astype(np.int64))
+    assert (sf.LabelLUT(z["cs_table"], device="cpu").table[35:] == 255).all()          # ids past the table -> ignore
+    with pytest.raises(SegFactoryError):
+        sf.LabelLUT(z["cs_table"], device="cpu")(torch.zeros(4, dtype=torch.uint8))
+    with pytest.raises(TypeError):
+        sf.LabelLUT(z["cs_table"], device="cpu")(torch.zeros(4, dtype=torch.int64))
+    with pytest.raises(ValueError):
+        sf.LabelLUT(np.arange(300))
