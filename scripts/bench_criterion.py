@@ -63,3 +63,5 @@ if __name__ == "__main__":
     run("cfg2 cityscapes 8x19x256x512->1024x2048 fp32 criterion(dice)", 8, 19, 256, 512, 1024, 2048, torch.float32, 1234)
     run("cfg3 16x150x128^2->512^2 fp32 criterion(dice)", 16, 150, 128, 128, 512, 512, torch.float32, 2345)
     run("cfg4 16x171 bf16 criterion(dice)", 16, 171, 128, 128, 512, 512, torch.bfloat16, 3456, eager=False)
+    # what an UNMODIFIED engine.py passes: the model has already upsampled (build_models.py:65), logits at label size
+    run("same-size 8x19x1024x2048 fp32 criterion(dice)", 8, 19, 1024, 2048, 1024, 2048, torch.float32, 1234, eager=False)

@@ -305,7 +305,7 @@ int launch_backward(const BwdArgs& a) {
 
     if (a.coef_a && (!a.coef_b || !a.dice_tb)) return SF_ERR_ARG;
     if (!env_no_fast()) {
-        int rc = a.coef_a ? -1000 : launch_backward_direct(a);     // logits already at label resolution (sf_direct.cu; no dice variant)
+        int rc = launch_backward_direct(a);                        // logits already at label resolution (sf_direct.cu)
         if (rc != -1000) return rc;
         rc = launch_backward_fast(a);                              // integer-scale specialisation (sf_backward_fast.cu)
         if (rc != -1000) return rc;

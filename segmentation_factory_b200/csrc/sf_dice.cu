@@ -277,7 +277,9 @@ static int launch_dice_walk(const FwdArgs& a, const DiceParams& d) {
     if (!env_no_fast()) {
         FwdArgs f = a;
         f.dice_mode = MODE; f.dice = d;
-        const int rc = launch_forward_fast(f);                     // integer-scale specialisation (sf_forward_fast.cu)
+        int rc = launch_dice_direct(f);                            // logits already at label resolution (sf_direct.cu)
+        if (rc != -1000) return rc;
+        rc = launch_forward_fast(f);                               // integer-scale specialisation (sf_forward_fast.cu)
         if (rc != -1000) return rc;
     }
     const int nch = pick_nch(a.C);

@@ -54,6 +54,7 @@ struct DirParams {
     const void* logits; const void* labels; const float* class_w;
     float* loss_px; float* lse_px; unsigned long long* hist; Workspace* ws;
     const float* loss_in; const float* lse_in; const float* grad_out; void* grad;
+    DiceArgs dice;              // dice walks (stats / coef) and, with coef_a/coef_b/tb set, the CE + dice backward
     long long plane;            // H*W (multiple of 4)
     long long n_quads;          // B*H*W / 4
     int C, ignore, label_u8;
@@ -177,17 +178,18 @@ fwd_direct_kernel(const DirParams p) {
     }
 }
 
-template <typename LT>
+// DICE: d/dz_k = g [p_k (A + tb[b][k]) - [k == y] Bc] with the per-pixel A, Bc of the coef walk (engine.criterion).
+template <typename LT, bool DICE>
 __global__ void __launch_bounds__(kDirThreads)
 bwd_direct_kernel(const DirParams p) {
     __shared__ float cw_s[256];
     const int tid = threadIdx.x, C = p.C;
     cw_s[tid] = (p.class_w && tid < C) ? __ldg(p.class_w + tid) : 1.0f;
     __syncthreads();
-    const sf_loss_state* stp = &p.ws->state;
-    const int branch = stp->branch;
-    const float kth = stp->kth, tie = stp->tie_share;
-    const float gscale = (p.grad_out ? __ldg(p.grad_out) : 1.0f) * stp->inv_denom;
+    const sf_loss_state* stp = &p.ws->state;                        // DICE: never dereferenced
+    const int branch = DICE ? 0 : stp->branch;
+    const float kth = DICE ? 0.f : stp->kth, tie = DICE ? 0.f : stp->tie_share;
+    const float gscale = (p.grad_out ? __ldg(p.grad_out) : 1.0f) * (DICE ? 1.0f : stp->inv_denom);
     const LT* logits = reinterpret_cast<const LT*>(p.logits);
     LT* grad = reinterpret_cast<LT*>(p.grad);
     const long long stride = (long long)gridDim.x * kDirThreads;
@@ -195,13 +197,25 @@ bwd_direct_kernel(const DirParams p) {
         const long long px = qd * kDirVec;
         const long long b = px / p.plane, off = px - b * p.plane;
         const long long base = b * C * p.plane + off;
-        float coef[kDirVec], cf[kDirVec], lse2[kDirVec];
+        float coef[kDirVec], cf[kDirVec], lse2[kDirVec], uf[kDirVec], cbv[kDirVec];
         int lab[kDirVec];
+        const float* tbb = DICE ? p.dice.tb + b * C : nullptr;
         #pragma unroll
         for (int v = 0; v < kDirVec; ++v) {
             const long long y = ld_label(p.labels, p.label_u8, px + v);
-            coef[v] = 0.f; cf[v] = 0.f; lse2[v] = 0.f; lab[v] = -1;
-            if (y != p.ignore && y >= 0 && y < C) {
+            coef[v] = 0.f; cf[v] = 0.f; lse2[v] = 0.f; lab[v] = -1; uf[v] = 0.f; cbv[v] = 0.f;
+            if (DICE) {
+                if (y != p.ignore && y >= 0 && y < C) {
+                    const float lse = __ldg(p.lse_in + px + v);
+                    lse2[v] = __fmul_rn(lse, kLog2e);
+                    const float pf = __fmaf_rn(-__fmaf_rn(lse, kLog2e, -lse2[v]), kLn2, 1.0f);
+                    coef[v] = 1.f;                                   // marks the pixel live
+                    cf[v] = __ldg(p.dice.coef_a + px + v) * gscale * pf;
+                    uf[v] = gscale * pf;
+                    cbv[v] = __ldg(p.dice.coef_b + px + v) * gscale;
+                    lab[v] = (int)y;
+                }
+            } else if (y != p.ignore && y >= 0 && y < C) {
                 float keep = 1.f;
                 if (branch != 0) { const float l = __ldg(p.loss_in + px + v); keep = branch == 3 ? l : (l > kth ? 1.f : (l == kth ? tie : 0.f)); }
                 if (keep != 0.f) {
@@ -217,12 +231,110 @@ bwd_direct_kernel(const DirParams p) {
         for (int c = 0; c < C; ++c) {
             float z[kDirVec], g[kDirVec];
             Vec4<LT>::ld(logits + base + (long long)c * p.plane, z);
+            const float tbc = DICE ? __ldg(tbb + c) : 0.f;
             #pragma unroll
             for (int v = 0; v < kDirVec; ++v) {
                 const float pc = coef[v] != 0.f ? ex2_approx(__fmaf_rn(z[v], kLog2e, -lse2[v])) : 0.f;
-                g[v] = __fmaf_rn(pc, cf[v], c == lab[v] ? -coef[v] : 0.f);
+                if (DICE) g[v] = __fmaf_rn(pc, __fmaf_rn(tbc, uf[v], cf[v]), c == lab[v] ? -cbv[v] : 0.f);
+                else g[v] = __fmaf_rn(pc, cf[v], c == lab[v] ? -coef[v] : 0.f);
             }
             Vec4<LT>::st(grad + base + (long long)c * p.plane, g);
+        }
+    }
+}
+
+// Dice walks of engine.criterion on same-size logits (see sf_dice.cu for the scheme).  One CTA column per image
+// (blockIdx.y = b), so the shared bins belong to one image; everything else streams like the kernels above.
+// MODE DICE_STATS: per class sum p_c (2^40 fixed point, REDUX over the warp, 64-bit shared/global integer atomics),
+// sum p_y [y == c] (2^26 per pixel) and the label counts.  MODE DICE_COEF: G = sum_j tb_j p_j -> coef_a, coef_b.
+template <typename LT, int MODE>
+__global__ void __launch_bounds__(kDirThreads)
+dice_direct_kernel(const DirParams p) {
+    extern __shared__ unsigned long long bins[];                     // STATS: [3][C]
+    __shared__ float cw_s[256], ta_s[256], tb_s[256];
+    const int tid = threadIdx.x, C = p.C, lane = tid & 31;
+    const int b = blockIdx.y;
+    if (MODE == DICE_STATS)
+        for (int k = tid; k < 3 * C; k += kDirThreads) bins[k] = 0ull;
+    cw_s[tid] = (p.class_w && tid < C) ? __ldg(p.class_w + tid) : 1.0f;
+    if (MODE == DICE_COEF) {
+        ta_s[tid] = tid < C ? __ldg(p.dice.ta + (long long)b * C + tid) : 0.f;
+        tb_s[tid] = tid < C ? __ldg(p.dice.tb + (long long)b * C + tid) : 0.f;
+    }
+    __syncthreads();
+    const float inv_denom = (MODE == DICE_COEF && p.ws) ? p.ws->state.inv_denom : 0.f;
+    const LT* logits = reinterpret_cast<const LT*>(p.logits) + (long long)b * C * p.plane;
+    const long long q_img = p.plane / kDirVec;
+    const long long stride = (long long)gridDim.x * kDirThreads;
+    const long long n_round = (q_img + 31) / 32 * 32;                // whole warps stay in the loop (match_any / redux)
+
+    for (long long qd = (long long)blockIdx.x * kDirThreads + tid; qd < n_round; qd += stride) {
+        const bool live = qd < q_img;
+        const long long off = (live ? qd : 0) * kDirVec;
+        const long long px = (long long)b * p.plane + off;
+        int lab[kDirVec];
+        float lse2[kDirVec], pcf[kDirVec], py[kDirVec], G[kDirVec];
+        #pragma unroll
+        for (int v = 0; v < kDirVec; ++v) {
+            const long long y = live ? ld_label(p.labels, p.label_u8, px + v) : -1;
+            lab[v] = (y != p.ignore && y >= 0 && y < C) ? (int)y : -1;
+            lse2[v] = 0.f; pcf[v] = 0.f; py[v] = 0.f; G[v] = 0.f;
+            if (lab[v] >= 0) {
+                const float lse = __ldg(p.dice.lse_in + px + v);
+                lse2[v] = __fmul_rn(lse, kLog2e);
+                pcf[v] = __fmaf_rn(-__fmaf_rn(lse, kLog2e, -lse2[v]), kLn2, 1.0f);
+            }
+        }
+        const bool any_valid = __any_sync(0xffffffffu, lab[0] >= 0 || lab[1] >= 0 || lab[2] >= 0 || lab[3] >= 0);
+        if (any_valid) {
+            #pragma unroll 4
+            for (int c = 0; c < C; ++c) {
+                float z[kDirVec];
+                Vec4<LT>::ld(logits + off + (long long)c * p.plane, z);
+                float sum4 = 0.f;
+                #pragma unroll
+                for (int v = 0; v < kDirVec; ++v) {
+                    const float pk = lab[v] >= 0 ? ex2_approx(__fmaf_rn(z[v], kLog2e, -lse2[v])) * pcf[v] : 0.f;
+                    if (c == lab[v]) py[v] = pk;
+                    if (MODE == DICE_STATS) sum4 += pk; else G[v] = fmaf(tb_s[c], pk, G[v]);
+                }
+                if (MODE == DICE_STATS) {
+                    const unsigned long long f = __float2ull_rn(sum4 * 1099511627776.f);       // <= 4 * 2^40
+                    const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)(f & 0xFFFFFull));
+                    const unsigned hi = __reduce_add_sync(0xffffffffu, (unsigned)(f >> 20));
+                    if (lane == 0) {
+                        const unsigned long long tot = ((unsigned long long)hi << 20) + lo;
+                        if (tot) atomicAdd(&bins[c], tot);
+                    }
+                }
+            }
+        }
+        #pragma unroll
+        for (int v = 0; v < kDirVec; ++v) {
+            if (MODE == DICE_STATS) {
+                const int key = lab[v];
+                const unsigned peers = __match_any_sync(0xffffffffu, key);
+                const unsigned sum = __reduce_add_sync(peers, key >= 0 ? __float2uint_rn(py[v] * 67108864.f) : 0u);
+                if (key >= 0 && lane == __ffs(peers) - 1) {
+                    atomicAdd(&bins[C + key], (unsigned long long)sum);
+                    atomicAdd(&bins[2 * C + key], (unsigned long long)__popc(peers));
+                }
+            } else if (live) {
+                float ca = 0.f, cb = 0.f;
+                if (lab[v] >= 0) {
+                    cb = fmaf(ta_s[lab[v]], py[v], inv_denom * cw_s[lab[v]]);
+                    ca = cb - G[v];
+                }
+                p.dice.coef_a[px + v] = ca;
+                p.dice.coef_b[px + v] = cb;
+            }
+        }
+    }
+    if (MODE == DICE_STATS) {
+        __syncthreads();
+        for (int k = tid; k < 3 * C; k += kDirThreads) {
+            const unsigned long long v = bins[k];
+            if (v) atomicAdd(p.dice.stats + ((long long)b * C + k % C) * 3 + k / C, v);
         }
     }
 }
@@ -262,9 +374,32 @@ int launch_forward_direct(const FwdArgs& a) {
     return (int)cudaGetLastError();
 }
 
+int launch_dice_direct(const FwdArgs& a) {
+    if (!direct_ok(a.h, a.w, a.H, a.W, a.C, a.logits, a.ldtype, nullptr) || a.B > 65535) return -1000;
+    DirParams p{};
+    p.logits = a.logits; p.labels = a.labels; p.class_w = a.class_w; p.ws = reinterpret_cast<Workspace*>(a.ws);
+    p.dice = a.dice;
+    p.plane = (long long)a.H * a.W; p.n_quads = (long long)a.B * p.plane / kDirVec;
+    p.C = a.C; p.ignore = a.ignore; p.label_u8 = a.ydtype == SF_U8;
+    const long long want = (p.plane / kDirVec + kDirThreads - 1) / kDirThreads;
+    const int gx = (int)std::max<long long>(1, std::min<long long>(want, (8LL * sm_count() + a.B - 1) / a.B));
+    const dim3 grid(gx, a.B);
+    const size_t smem = a.dice_mode == DICE_STATS ? (size_t)3 * a.C * 8 : 0;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(a.stream);
+#define SF_LAUNCH(LT)                                                                                               \
+    {                                                                                                               \
+        if (a.dice_mode == DICE_STATS) dice_direct_kernel<LT, DICE_STATS><<<grid, kDirThreads, smem, st>>>(p);      \
+        else dice_direct_kernel<LT, DICE_COEF><<<grid, kDirThreads, smem, st>>>(p);                                 \
+    }
+    if (a.ldtype == SF_F32) SF_LAUNCH(float) else if (a.ldtype == SF_BF16) SF_LAUNCH(__nv_bfloat16) else SF_LAUNCH(__half)
+#undef SF_LAUNCH
+    return (int)cudaGetLastError();
+}
+
 int launch_backward_direct(const BwdArgs& a) {
     if (!direct_ok(a.h, a.w, a.H, a.W, a.C, a.logits, a.ldtype, a.grad_logits)) return -1000;
     DirParams p{};
+    p.dice.coef_a = const_cast<float*>(a.coef_a); p.dice.coef_b = const_cast<float*>(a.coef_b); p.dice.tb = a.dice_tb;
     p.logits = a.logits; p.labels = a.labels; p.class_w = a.class_w; p.loss_in = a.loss_px; p.lse_in = a.lse_px;
     p.grad_out = a.grad_out; p.ws = const_cast<Workspace*>(reinterpret_cast<const Workspace*>(a.ws)); p.grad = a.grad_logits;
     p.plane = (long long)a.H * a.W; p.n_quads = (long long)a.B * p.plane / kDirVec;
@@ -272,9 +407,15 @@ int launch_backward_direct(const BwdArgs& a) {
     const long long want = (p.n_quads + kDirThreads - 1) / kDirThreads;
     const int grid = (int)std::min<long long>(want, 8LL * sm_count());
     cudaStream_t st = reinterpret_cast<cudaStream_t>(a.stream);
-    if (a.ldtype == SF_F32) bwd_direct_kernel<float><<<grid, kDirThreads, 0, st>>>(p);
-    else if (a.ldtype == SF_BF16) bwd_direct_kernel<__nv_bfloat16><<<grid, kDirThreads, 0, st>>>(p);
-    else bwd_direct_kernel<__half><<<grid, kDirThreads, 0, st>>>(p);
+    if (a.coef_a) {
+        if (a.ldtype == SF_F32) bwd_direct_kernel<float, true><<<grid, kDirThreads, 0, st>>>(p);
+        else if (a.ldtype == SF_BF16) bwd_direct_kernel<__nv_bfloat16, true><<<grid, kDirThreads, 0, st>>>(p);
+        else bwd_direct_kernel<__half, true><<<grid, kDirThreads, 0, st>>>(p);
+    } else {
+        if (a.ldtype == SF_F32) bwd_direct_kernel<float, false><<<grid, kDirThreads, 0, st>>>(p);
+        else if (a.ldtype == SF_BF16) bwd_direct_kernel<__nv_bfloat16, false><<<grid, kDirThreads, 0, st>>>(p);
+        else bwd_direct_kernel<__half, false><<<grid, kDirThreads, 0, st>>>(p);
+    }
     return (int)cudaGetLastError();
 }
 

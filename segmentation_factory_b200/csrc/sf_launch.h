@@ -37,6 +37,7 @@ struct FwdArgs {
 int launch_forward(const FwdArgs& a);
 int launch_forward_fast(const FwdArgs& a);    // -1000: shape not covered by the integer-scale specialisation
 int launch_forward_direct(const FwdArgs& a);  // h == H, w == W: streaming kernels, no interpolation; -1000: not covered
+int launch_dice_direct(const FwdArgs& a);     // dice walks on same-size logits (a.dice_mode, a.dice); -1000: not covered
 int launch_forward_chunk(const FwdArgs& a);   // integer scale, many classes (16-class chunks); -1000: not covered
 
 struct BwdArgs {

@@ -51,6 +51,9 @@ DICE_CASES = [
     ("downscale", 107, 1, 7, 150, 130, 100, 90, "early", torch.float32, torch.int64, False),
     ("identity", 108, 1, 19, 96, 128, 96, 128, "late", torch.float32, torch.int64, False),
     ("binary", 109, 3, 2, 32, 64, 128, 256, "early", torch.float32, torch.int64, True),
+    ("fullres_bf16_c150_u8", 110, 2, 150, 64, 80, 64, 80, "early", torch.bfloat16, torch.uint8, True),
+    ("fullres_fp16_late", 112, 3, 21, 96, 128, 96, 128, "late", torch.float16, torch.int64, False),
+    ("fullres_fp32_weighted", 113, 2, 19, 128, 160, 128, 160, "late", torch.float32, torch.int64, True),
 ]
 
 
