@@ -16,6 +16,7 @@
 // arrive: bitwise reproducible without a fixed-order reduction tree.  sum p_c: per-thread fp32 partial over <= 4
 // pixels -> 2^40 fixed point -> two 32-bit warp reductions (REDUX) -> one 64-bit shared atomic per warp and class;
 // inter: 2^26 fixed point per pixel, warp-aggregated per label with __match_any_sync; counts are exact.
+#include "sf_dice_bins.cuh"
 #include "sf_fwd_generic.cuh"
 
 namespace sf {
@@ -31,15 +32,14 @@ __global__ void __launch_bounds__(kFwdThreads, 2)
 dice_kernel(const __grid_constant__ CUtensorMap tmap, const FwdParams p, const DiceParams d) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* stages = smem;
-    unsigned long long* bins = reinterpret_cast<unsigned long long*>(smem + kFwdStages * p.stage_bytes);   // [3][C]
+    const DiceBins bins{reinterpret_cast<unsigned*>(smem + kFwdStages * p.stage_bytes), p.C};
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + kFwdStages * p.stage_bytes + p.hist_bytes);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int tx = tid % kFwdTW, gy = tid / kFwdTW;
 
-    if (MODE == DICE_STATS)
-        for (int k = tid; k < 3 * p.C; k += kFwdThreads) bins[k] = 0ull;
+    if (MODE == DICE_STATS) bins.zero(tid, kFwdThreads);
     if (tid == 0 && p.use_tma) {
         tma_prefetch_desc(&tmap);
         for (int s = 0; s < kFwdStages; ++s) mbar_init(&full[s], 1);
@@ -58,15 +58,8 @@ dice_kernel(const __grid_constant__ CUtensorMap tmap, const FwdParams p, const D
 
     const float inv_denom = (MODE == DICE_COEF && p.ws) ? p.ws->state.inv_denom : 0.f;
 
-    auto flush = [&](int b) {                       // CTA-uniform: image b's bins -> global, bins = 0
-        __syncthreads();
-        for (int k = tid; k < 3 * p.C; k += kFwdThreads) {
-            const unsigned long long v = bins[k];
-            if (v) atomicAdd(d.stats + ((long long)b * p.C + k % p.C) * 3 + k / p.C, v);
-            bins[k] = 0ull;
-        }
-        __syncthreads();
-    };
+    auto flush = [&](int b) { bins.flush(d.stats, b, tid, kFwdThreads); };   // CTA-uniform
+    int since_flush = 0;
     int cur_b = -1;
 
     int X = 0, j0r = 0, j1r = 0, r0 = 0, r1 = 0, nrows = 0, Yb = 0;
@@ -81,8 +74,9 @@ dice_kernel(const __grid_constant__ CUtensorMap tmap, const FwdParams p, const D
         LT* S = reinterpret_cast<LT*>(stages + stage * p.stage_bytes);
 
         if (c.chunk == 0) {
-            if (MODE == DICE_STATS && c.pass == 0 && c.b != cur_b) {
-                if (cur_b >= 0) flush(cur_b);
+            if (MODE == DICE_STATS && c.pass == 0) {
+                // a limb word takes <= 8 warps x 4 rows x n_passes adds per tile
+                if (cur_b >= 0 && (c.b != cur_b || (since_flush += 32 * p.n_passes) >= kDiceFlushAdds)) { flush(cur_b); since_flush = 0; }
                 cur_b = c.b;
             }
             X = c.Xa + tx;
@@ -167,10 +161,7 @@ dice_kernel(const __grid_constant__ CUtensorMap tmap, const FwdParams p, const D
                         const unsigned peers = __match_any_sync(0xffffffffu, key);
                         const unsigned v = key >= 0 ? __float2uint_rn(pyv * kFixI) : 0u;
                         const unsigned sum = __reduce_add_sync(peers, v);
-                        if (key >= 0 && lane == __ffs(peers) - 1) {
-                            atomicAdd(&bins[p.C + key], (unsigned long long)sum);
-                            atomicAdd(&bins[2 * p.C + key], (unsigned long long)__popc(peers));
-                        }
+                        if (key >= 0 && lane == __ffs(peers) - 1) bins.add_inter(key, sum, __popc(peers));
                     }
                 }
             }
@@ -180,10 +171,7 @@ dice_kernel(const __grid_constant__ CUtensorMap tmap, const FwdParams p, const D
                     const unsigned long long v = __float2ull_rn(aux[k] * kFixS);      // <= 4 * 2^40
                     const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)(v & 0xFFFFFull));
                     const unsigned hi = __reduce_add_sync(0xffffffffu, (unsigned)(v >> 20));
-                    if (lane == 0 && k < nvalid) {
-                        const unsigned long long tot = ((unsigned long long)hi << 20) + lo;
-                        if (tot) atomicAdd(&bins[c0 + k], tot);
-                    }
+                    if (lane == 0 && k < nvalid) bins.add_sum(c0 + k, ((unsigned long long)hi << 20) + lo);
                 }
             }
         }
@@ -280,6 +268,8 @@ static int launch_dice_walk(const FwdArgs& a, const DiceParams& d) {
         int rc = launch_dice_direct(f);                            // logits already at label resolution (sf_direct.cu)
         if (rc != -1000) return rc;
         rc = launch_forward_fast(f);                               // integer-scale specialisation (sf_forward_fast.cu)
+        if (rc != -1000) return rc;
+        rc = launch_forward_chunk(f);                              // integer scale, > 24 classes (sf_forward_chunk.cu)
         if (rc != -1000) return rc;
     }
     const int nch = pick_nch(a.C);

@@ -10,6 +10,7 @@
 //   * confusion counts: shared-memory C x C int32, warp-aggregated, one 64-bit flush per CTA;
 //   * backward: g = coef * (2^(z*log2e - lse*log2e) - [c == y]) written straight to grad (overwrites every element).
 #include "sf_common.cuh"
+#include "sf_dice_bins.cuh"
 #include "sf_launch.h"
 
 namespace sf {
@@ -250,12 +251,12 @@ bwd_direct_kernel(const DirParams p) {
 template <typename LT, int MODE>
 __global__ void __launch_bounds__(kDirThreads)
 dice_direct_kernel(const DirParams p) {
-    extern __shared__ unsigned long long bins[];                     // STATS: [3][C]
+    extern __shared__ unsigned bin_words[];                          // STATS: DiceBins
+    const DiceBins bins{bin_words, p.C};
     __shared__ float cw_s[256], ta_s[256], tb_s[256];
     const int tid = threadIdx.x, C = p.C, lane = tid & 31;
     const int b = blockIdx.y;
-    if (MODE == DICE_STATS)
-        for (int k = tid; k < 3 * C; k += kDirThreads) bins[k] = 0ull;
+    if (MODE == DICE_STATS) bins.zero(tid, kDirThreads);
     cw_s[tid] = (p.class_w && tid < C) ? __ldg(p.class_w + tid) : 1.0f;
     if (MODE == DICE_COEF) {
         ta_s[tid] = tid < C ? __ldg(p.dice.ta + (long long)b * C + tid) : 0.f;
@@ -268,7 +269,9 @@ dice_direct_kernel(const DirParams p) {
     const long long stride = (long long)gridDim.x * kDirThreads;
     const long long n_round = (q_img + 31) / 32 * 32;                // whole warps stay in the loop (match_any / redux)
 
+    int iters = 0;
     for (long long qd = (long long)blockIdx.x * kDirThreads + tid; qd < n_round; qd += stride) {
+        if (MODE == DICE_STATS && ++iters >= kDiceFlushAdds / 32) { bins.flush(p.dice.stats, b, tid, kDirThreads); iters = 0; }   // 8 warps x 4 adds
         const bool live = qd < q_img;
         const long long off = (live ? qd : 0) * kDirVec;
         const long long px = (long long)b * p.plane + off;
@@ -302,10 +305,7 @@ dice_direct_kernel(const DirParams p) {
                     const unsigned long long f = __float2ull_rn(sum4 * 1099511627776.f);       // <= 4 * 2^40
                     const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)(f & 0xFFFFFull));
                     const unsigned hi = __reduce_add_sync(0xffffffffu, (unsigned)(f >> 20));
-                    if (lane == 0) {
-                        const unsigned long long tot = ((unsigned long long)hi << 20) + lo;
-                        if (tot) atomicAdd(&bins[c], tot);
-                    }
+                    if (lane == 0) bins.add_sum(c, ((unsigned long long)hi << 20) + lo);
                 }
             }
         }
@@ -315,10 +315,7 @@ dice_direct_kernel(const DirParams p) {
                 const int key = lab[v];
                 const unsigned peers = __match_any_sync(0xffffffffu, key);
                 const unsigned sum = __reduce_add_sync(peers, key >= 0 ? __float2uint_rn(py[v] * 67108864.f) : 0u);
-                if (key >= 0 && lane == __ffs(peers) - 1) {
-                    atomicAdd(&bins[C + key], (unsigned long long)sum);
-                    atomicAdd(&bins[2 * C + key], (unsigned long long)__popc(peers));
-                }
+                if (key >= 0 && lane == __ffs(peers) - 1) bins.add_inter(key, sum, __popc(peers));
             } else if (live) {
                 float ca = 0.f, cb = 0.f;
                 if (lab[v] >= 0) {
@@ -330,13 +327,7 @@ dice_direct_kernel(const DirParams p) {
             }
         }
     }
-    if (MODE == DICE_STATS) {
-        __syncthreads();
-        for (int k = tid; k < 3 * C; k += kDirThreads) {
-            const unsigned long long v = bins[k];
-            if (v) atomicAdd(p.dice.stats + ((long long)b * C + k % C) * 3 + k / C, v);
-        }
-    }
+    if (MODE == DICE_STATS) bins.flush(p.dice.stats, b, tid, kDirThreads);
 }
 
 static bool direct_ok(int h, int w, int H, int W, int C, const void* logits, int ldtype, const void* grad) {

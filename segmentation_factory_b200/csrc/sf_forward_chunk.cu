@@ -11,6 +11,7 @@
 // The C x C int32 histogram (90-118 KB for 150-172 classes) shares the SM's shared memory with the ring, hence one
 // 512-thread CTA per SM when the matrix is requested.
 #include "sf_fast.cuh"
+#include "sf_dice_bins.cuh"
 #include "sf_launch.h"
 
 namespace sf {
@@ -27,7 +28,10 @@ struct FcParams {
     int B, C, h, w, H, W, ignore, label_u8;
     float thresh;
     int tiles_x, tiles_y, total_tiles, n_chunks, hist_bytes;
+    DiceArgs dice;                                                  // MODE >= 2 (sf_dice.cu)
 };
+
+enum { FC_ARGMAX = 0, FC_SOFTMAX = 1, FC_DICE_STATS = 2, FC_DICE_COEF = 3 };
 
 template <typename LT, int S>
 struct FcGeom {
@@ -39,12 +43,16 @@ struct FcGeom {
     static constexpr int STAGE_BYTES = round_up(kFcNCH * PLANE * (int)sizeof(LT), 128);
 };
 
-template <typename LT, int S, bool SOFTMAX>
+// MODE: FC_ARGMAX / FC_SOFTMAX are the forward proper; FC_DICE_STATS / FC_DICE_COEF are the dice walks of sf_dice.cu
+// (softmax from the stored lse: no running max, no argmax, no histogram).
+template <typename LT, int S, int MODE>
 __global__ void __launch_bounds__(kFcThreads, 1)
 fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmap, const FcParams p) {
     using G = FcGeom<LT, S>;
     using TP = ScaleTap<S>;
     constexpr int NP = kFcNP;
+    constexpr bool SOFTMAX = MODE == FC_SOFTMAX;
+    constexpr bool DSTAT = MODE == FC_DICE_STATS, DCOEF = MODE == FC_DICE_COEF, DICE = DSTAT || DCOEF;
     extern __shared__ __align__(128) unsigned char smem[];
     int* hist_s = reinterpret_cast<int*>(smem + kFcStages * G::STAGE_BYTES);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + kFcStages * G::STAGE_BYTES + p.hist_bytes);
@@ -53,12 +61,26 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmap, const FcParams p) {
 
     const int tid = threadIdx.x;
     const int tx = tid % kFcTW, sy = tid / kFcTW;
-    const bool want_hist = p.hist != nullptr;
+    const bool want_hist = !DICE && p.hist != nullptr;
     const unsigned lane_lt = (1u << (tid & 31)) - 1u;
     const int C = p.C;
+    const int CP = C + (C & 1);                                     // even pitch of the per-image dice tables
+    const DiceBins bins{reinterpret_cast<unsigned*>(hist_s), C};                        // DSTAT
+    float* tab_s = reinterpret_cast<float*>(full + kFcStages);                          // DCOEF: ta[B][CP], tb[B][CP + 16]
 
     if (want_hist)
         for (int k = tid; k < C * C; k += kFcThreads) hist_s[k] = 0;
+    if (DSTAT) bins.zero(tid, kFcThreads);
+    const int TBP = CP + kFcNCH;                                    // tb rows are padded so a tail chunk reads zeros
+    if (DCOEF) {
+        for (int k = tid; k < p.B * CP; k += kFcThreads) tab_s[k] = (k % CP) < C ? __ldg(p.dice.ta + (k / CP) * C + k % CP) : 0.f;
+        for (int k = tid; k < p.B * TBP; k += kFcThreads) tab_s[p.B * CP + k] = (k % TBP) < C ? __ldg(p.dice.tb + (k / TBP) * C + k % TBP) : 0.f;
+    }
+    const float* tb_s = tab_s + p.B * CP;
+    const float inv_denom = (DCOEF && p.ws) ? p.ws->state.inv_denom : 0.f;
+    int cur_b = -1;
+    auto flush_bins = [&](int bb) { bins.flush(p.dice.stats, bb, tid, kFcThreads); };   // CTA-uniform
+    int tiles_in_bins = 0;
     if (tid < 256) cw_s[tid] = (p.class_w && tid < C) ? __ldg(p.class_w + tid) : 1.0f;
     if (tid == 0) {
         tma_prefetch_desc(&tmap);
@@ -97,6 +119,7 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmap, const FcParams p) {
     unsigned nanlock = 0;
     float m[S], s[S], zy[S];
     int idx[S];
+    float lse2[DICE ? S : 1], pcf[DICE ? S : 1], Gs[DICE ? S : 1], py[DICE ? S : 1];
 
     for (int n = 0; n < n_items; ++n) {
         const int chunk = n % p.n_chunks;
@@ -105,6 +128,10 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmap, const FcParams p) {
         if (chunk == 0) {
             const int tile = blockIdx.x + (n / p.n_chunks) * gridDim.x;
             b = tile / per_img;
+            if (DSTAT) {                                             // a limb word takes <= 16 warps x S rows adds per tile
+                if (cur_b >= 0 && (b != cur_b || tiles_in_bins >= kDiceFlushAdds / (16 * S))) { flush_bins(cur_b); tiles_in_bins = 0; }
+                cur_b = b; ++tiles_in_bins;
+            }
             const int rr = tile % per_img;
             ua = -1 + (rr / p.tiles_x) * G::NGT;
             const int Xa = (rr % p.tiles_x) * kFcTW;
@@ -128,12 +155,114 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmap, const FcParams p) {
                         if (y != p.ignore && y >= 0 && y < C) v = (unsigned)y;
                     }
                     labs |= (unsigned long long)v << (8 * r);
+                    if (DICE) {
+                        lse2[r] = 0.f; pcf[r] = 0.f; Gs[r] = 0.f; py[r] = 0.f;
+                        if (v != 255u) {
+                            const float lse = __ldg(p.dice.lse_in + base + (long long)r * p.W);
+                            lse2[r] = __fmul_rn(lse, kLog2e);
+                            pcf[r] = __fmaf_rn(-__fmaf_rn(lse, kLog2e, -lse2[r]), kLn2, 1.0f);
+                        }
+                    }
                 }
             }
         }
 
         mbar_wait(&full[n % kFcStages], (uint32_t)((n / kFcStages) & 1));
 
+        if (DICE) {
+            // warp-uniform guard (a warp shares sy): the reductions below need every lane, idle columns carry no valid pixel
+            const int rows = (u <= p.h - 1) ? TP::count(u, p.h) : 0;
+            if (rows > 0) {
+                const int c0 = chunk * kFcNCH;
+                const int nvalid = min(kFcNCH, C - c0);
+                const LT* q00 = Sg + (i0 - ua) * G::BW + (j0 - jO);
+                const LT* q01 = Sg + (i0 - ua) * G::BW + (j1 - jO);
+                const LT* q10 = Sg + (i1 - ua) * G::BW + (j0 - jO);
+                const LT* q11 = Sg + (i1 - ua) * G::BW + (j1 - jO);
+                const float2 lw0_2 = splat(lw0), lw1_2 = splat(lw1);
+                float2 top[NP], bot[NP], accp[NP];
+                #pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    const float2 a = make_float2(Logit<LT>::ld(q00 + (2 * q) * G::PLANE), Logit<LT>::ld(q00 + (2 * q + 1) * G::PLANE));
+                    const float2 c = make_float2(Logit<LT>::ld(q01 + (2 * q) * G::PLANE), Logit<LT>::ld(q01 + (2 * q + 1) * G::PLANE));
+                    top[q] = lerp2_pinned(a, lw0_2, c, lw1_2);
+                    const float2 d = make_float2(Logit<LT>::ld(q10 + (2 * q) * G::PLANE), Logit<LT>::ld(q10 + (2 * q + 1) * G::PLANE));
+                    const float2 e = make_float2(Logit<LT>::ld(q11 + (2 * q) * G::PLANE), Logit<LT>::ld(q11 + (2 * q + 1) * G::PLANE));
+                    bot[q] = lerp2_pinned(d, lw0_2, e, lw1_2);
+                    accp[q] = make_float2(0.f, 0.f);
+                }
+                #pragma unroll
+                for (int r = 0; r < S; ++r) {
+                    if (r < rows) {
+                        const int lab = (int)((labs >> (8 * r)) & 0xffu);
+                        const bool valid = cnt > 0 && lab != 255;
+                        const float lh1 = u < 0 ? 0.0f : ((float)r + 0.5f) * (1.0f / S);
+                        const float lh0 = 1.0f - lh1;
+                        const float pv = valid ? pcf[r] : 0.f;
+                        const float l2 = valid ? lse2[r] : 0.f;
+                        if (__any_sync(0xffffffffu, valid)) {
+                            const float2 lh0_2 = splat(lh0), lh1_2 = splat(lh1), nl2 = splat(-l2), pv2 = splat(pv);
+                            float2 g2 = make_float2(0.f, 0.f);
+                            #pragma unroll
+                            for (int q = 0; q < NP; ++q) {
+                                float2 z = rnd2<LT>(lerp2_pinned(top[q], lh0_2, bot[q], lh1_2));
+                                if (2 * q >= nvalid) z.x = -INFINITY;            // classes past C add nothing
+                                if (2 * q + 1 >= nvalid) z.y = -INFINITY;
+                                const float2 e = __ffma2_rn(z, l2e2, nl2);
+                                const float2 ex = make_float2(ex2_approx(e.x), ex2_approx(e.y));
+                                if (DSTAT) accp[q] = __ffma2_rn(ex, pv2, accp[q]);
+                                else g2 = __ffma2_rn(ex, *reinterpret_cast<const float2*>(tb_s + b * TBP + c0 + 2 * q), g2);
+                            }
+                            if (DCOEF) Gs[r] = fmaf(g2.x + g2.y, pv, Gs[r]);
+                        }
+                        const int yk = lab - c0;
+                        const bool mine = valid && yk >= 0 && yk < nvalid;     // this chunk holds the label's class
+                        float pyv = 0.f;
+                        if (mine) {                                              // label logit: same ops as its z[] entry
+                            const float t0 = lerp_pinned(Logit<LT>::ld(q00 + yk * G::PLANE), lw0, Logit<LT>::ld(q01 + yk * G::PLANE), lw1);
+                            const float t1 = lerp_pinned(Logit<LT>::ld(q10 + yk * G::PLANE), lw0, Logit<LT>::ld(q11 + yk * G::PLANE), lw1);
+                            const float zyv = Logit<LT>::rnd(lerp_pinned(t0, lh0, t1, lh1));
+                            pyv = ex2_approx(__fmaf_rn(zyv, kLog2e, -l2)) * pv;
+                            if (DCOEF) py[r] = pyv;
+                        }
+                        if (DSTAT) {
+                            const int key = mine ? lab : -1;
+                            const unsigned peers = __match_any_sync(0xffffffffu, key);
+                            const unsigned sum = __reduce_add_sync(peers, mine ? __float2uint_rn(pyv * 67108864.f) : 0u);
+                            if (mine && (peers & lane_lt) == 0) bins.add_inter(lab, sum, __popc(peers));
+                        }
+                    }
+                }
+                if (DSTAT) {                                          // this item's partial sums (<= S pixels per lane) -> shared bins
+                    #pragma unroll
+                    for (int q = 0; q < NP; ++q) {
+                        #pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const unsigned long long f = __float2ull_rn((hh ? accp[q].y : accp[q].x) * 1099511627776.f);
+                            const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)(f & 0xFFFFFull));
+                            const unsigned hi = __reduce_add_sync(0xffffffffu, (unsigned)(f >> 20));
+                            if (lane_lt == 0 && 2 * q + hh < nvalid) bins.add_sum(c0 + 2 * q + hh, ((unsigned long long)hi << 20) + lo);
+                        }
+                    }
+                }
+                if (DCOEF && chunk == p.n_chunks - 1 && cnt > 0) {
+                    const long long px0 = ((long long)b * p.H + TP::first(u)) * p.W + X;
+                    #pragma unroll
+                    for (int r = 0; r < S; ++r) {
+                        if (r < cnt) {
+                            const int lab = (int)((labs >> (8 * r)) & 0xffu);
+                            float ca = 0.f, cb = 0.f;
+                            if (lab != 255) {
+                                cb = fmaf(tab_s[b * CP + lab], py[r], inv_denom * cw_s[lab]);
+                                ca = cb - Gs[r];
+                            }
+                            p.dice.coef_a[px0 + (long long)r * p.W] = ca;
+                            p.dice.coef_b[px0 + (long long)r * p.W] = cb;
+                        }
+                    }
+                }
+            }
+        } else
         if (cnt > 0) {
             const int c0 = chunk * kFcNCH;
             const int nvalid = min(kFcNCH, C - c0);
@@ -222,7 +351,7 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmap, const FcParams p) {
             }
         }
 
-        if (chunk == p.n_chunks - 1) {
+        if (!DICE && chunk == p.n_chunks - 1) {
             // ---- tile epilogue: per-pixel outputs, histogram, loss sums ----
             const long long px0 = ((long long)b * p.H + TP::first(min(u, p.h - 1))) * p.W + X;
             float tile_loss = 0.f, tile_w = 0.f, tile_hard = 0.f;
@@ -261,6 +390,7 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmap, const FcParams p) {
         if (tid == 0 && n + kFcStages < n_items) issue(n + kFcStages);
     }
 
+    if (DSTAT && cur_b >= 0) flush_bins(cur_b);
     if (want_hist) {
         for (int k = tid; k < C * C; k += kFcThreads) {
             const int v = hist_s[k];
@@ -284,7 +414,7 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmap, const FcParams p) {
 // ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
-template <typename LT, int S, bool SOFTMAX>
+template <typename LT, int S, int MODE>
 static int fc_launch(const FwdArgs& a) {
     using G = FcGeom<LT, S>;
     if (a.w < G::BW || a.h < G::BH) return -1000;                   // the TMA box must fit inside the tensor
@@ -292,20 +422,25 @@ static int fc_launch(const FwdArgs& a) {
     p.labels = a.labels; p.class_w = a.class_w; p.loss_px = a.loss_px; p.lse_px = a.lse_px; p.hist = a.hist;
     p.ws = reinterpret_cast<Workspace*>(a.ws);
     p.B = a.B; p.C = a.C; p.h = a.h; p.w = a.w; p.H = a.H; p.W = a.W; p.ignore = a.ignore; p.label_u8 = a.ydtype == SF_U8;
-    p.thresh = a.thresh;
+    p.thresh = a.thresh; p.dice = a.dice;
     p.tiles_x = (a.W + kFcTW - 1) / kFcTW;
     p.tiles_y = (a.h + 1 + G::NGT - 1) / G::NGT;
     p.n_chunks = (a.C + kFcNCH - 1) / kFcNCH;
     const long long total = (long long)a.B * p.tiles_x * p.tiles_y;
     if (total * p.n_chunks >= (1LL << 31)) return SF_ERR_SHAPE;
     p.total_tiles = (int)total;
-    p.hist_bytes = a.hist ? round_up(a.C * a.C * 4, 16) : 16;
-    const size_t smem = (size_t)kFcStages * G::STAGE_BYTES + p.hist_bytes + kFcStages * 8 + 16;
+    p.hist_bytes = MODE == FC_DICE_STATS ? round_up(3 * a.C * 8, 16) : (a.hist && MODE < 2) ? round_up(a.C * a.C * 4, 16) : 16;
+    size_t smem = (size_t)kFcStages * G::STAGE_BYTES + p.hist_bytes + kFcStages * 8 + 16;
+    if (MODE == FC_DICE_COEF) {
+        const size_t tab = (size_t)a.B * (2 * (a.C + (a.C & 1)) + kFcNCH) * 4;
+        if (tab > 64 * 1024) return -1000;                          // per-image tables live in shared memory
+        smem += tab;
+    }
     if (smem > 227 * 1024) return SF_ERR_TOO_MANY_CLASSES;
     CUtensorMap tmap{};
     const int rc = make_logits_tmap(&tmap, a.logits, a.ldtype, a.B * a.C, a.h, a.w, kFcNCH, G::BH, G::BW);
     if (rc != 0) return rc;
-    auto k = fwd_chunk_kernel<LT, S, SOFTMAX>;
+    auto k = fwd_chunk_kernel<LT, S, MODE>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int per_sm = 1;
@@ -318,7 +453,9 @@ static int fc_launch(const FwdArgs& a) {
 
 template <typename LT, int S>
 static int fc_mode(const FwdArgs& a) {
-    return a.softmax ? fc_launch<LT, S, true>(a) : fc_launch<LT, S, false>(a);
+    if (a.dice_mode == DICE_STATS) return fc_launch<LT, S, FC_DICE_STATS>(a);
+    if (a.dice_mode == DICE_COEF) return fc_launch<LT, S, FC_DICE_COEF>(a);
+    return a.softmax ? fc_launch<LT, S, FC_SOFTMAX>(a) : fc_launch<LT, S, FC_ARGMAX>(a);
 }
 template <typename LT>
 static int fc_scale(const FwdArgs& a, int s) {

@@ -15,6 +15,8 @@
 #include "sf_fast.cuh"
 #include <cstdlib>
 
+#include "sf_dice_bins.cuh"
+
 #include "sf_launch.h"
 
 namespace sf {
@@ -70,14 +72,13 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
     const int tx = tid % kFfTW, sy = tid / kFfTW;
     if (tid < 32) cw_s[tid] = (p.class_w && tid < C) ? __ldg(p.class_w + tid) : 1.0f;
     const bool want_hist = !DICE && p.hist != nullptr;
-    unsigned long long* bins = reinterpret_cast<unsigned long long*>(hist_s);          // DSTAT: [3][C] in the histogram area
+    const DiceBins bins{reinterpret_cast<unsigned*>(hist_s), C};                        // DSTAT: in the histogram area
     float* tab_s = reinterpret_cast<float*>(full + kFfStages);                          // DCOEF: ta[B][CP], tb[B][CP]
     const int lane = tid & 31;
 
     if (want_hist)
         for (int k = tid; k < C * C; k += kFfThreads) hist_s[k] = 0;
-    if (DSTAT)
-        for (int k = tid; k < 3 * C; k += kFfThreads) bins[k] = 0ull;
+    if (DSTAT) bins.zero(tid, kFfThreads);
     if (DCOEF)
         for (int k = tid; k < 2 * p.B * CP; k += kFfThreads) {
             const int which = k / (p.B * CP), r = k % (p.B * CP), bb = r / CP, cc = r % CP;
@@ -128,25 +129,18 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
         #pragma unroll
         for (int q = 0; q < NP; ++q) {
             const unsigned long long sx = redux3(accp[q].x), sy2 = redux3(accp[q].y);
-            if (lane == 0) { if (sx) atomicAdd(&bins[2 * q], sx); if (sy2) atomicAdd(&bins[2 * q + 1], sy2); }
+            if (lane == 0) { bins.add_sum(2 * q, sx); bins.add_sum(2 * q + 1, sy2); }
             accp[q] = make_float2(0.f, 0.f);
         }
         if (G::ODD) {
             const unsigned long long sl = redux3(accpl);
-            if (lane == 0 && sl) atomicAdd(&bins[C - 1], sl);
+            if (lane == 0) bins.add_sum(C - 1, sl);
             accpl = 0.f;
         }
         since_flush = 0;
     };
-    auto flush_bins = [&](int b) {                                   // CTA-uniform: image b's bins -> global
-        __syncthreads();
-        for (int k = tid; k < 3 * C; k += kFfThreads) {
-            const unsigned long long v = bins[k];
-            if (v) atomicAdd(p.dice.stats + ((long long)b * C + k % C) * 3 + k / C, v);
-            bins[k] = 0ull;
-        }
-        __syncthreads();
-    };
+    auto flush_bins = [&](int b) { bins.flush(p.dice.stats, b, tid, kFfThreads); };   // CTA-uniform
+    int tiles_in_bins = 0;
 
     for (int n = 0; n < n_tiles; ++n) {
         const int tile = blockIdx.x + n * gridDim.x;
@@ -156,9 +150,11 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
         if (DSTAT) {
             if (b != cur_b || since_flush >= 8) {                    // keep the fp32 partials short (<= 128 pixels)
                 flush_acc();
-                if (b != cur_b) { if (cur_b >= 0) flush_bins(cur_b); cur_b = b; }
+                // a limb word takes <= 8 warps x 16 rows adds per tile
+                if (cur_b >= 0 && (b != cur_b || tiles_in_bins >= kDiceFlushAdds / 128)) { flush_bins(cur_b); tiles_in_bins = 0; }
+                cur_b = b;
             }
-            ++since_flush;
+            ++since_flush; ++tiles_in_bins;
         }
         const int X = Xa + tx;
         const bool colok = X < p.W;
@@ -356,10 +352,7 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
                         const int key = valid ? lab : -1;
                         const unsigned peers = __match_any_sync(0xffffffffu, key);
                         const unsigned sum = __reduce_add_sync(peers, valid ? __float2uint_rn(py * 67108864.f) : 0u);
-                        if (valid && lane == __ffs(peers) - 1) {
-                            atomicAdd(&bins[C + lab], (unsigned long long)sum);
-                            atomicAdd(&bins[2 * C + lab], (unsigned long long)__popc(peers));
-                        }
+                        if (valid && lane == __ffs(peers) - 1) bins.add_inter(lab, sum, __popc(peers));
                     } else if (colok) {
                         float ca = 0.f, cb = 0.f;
                         if (valid) {
