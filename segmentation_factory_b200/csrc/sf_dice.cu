@@ -156,7 +156,7 @@ dice_kernel(const __grid_constant__ CUtensorMap tmap, const FwdParams p, const D
                             if (yk >= 0 && yk < nvalid) py[r] = pyv;
                         }
                     }
-                    if (MODE == DICE_STATS) {
+                    if (MODE == DICE_STATS && __any_sync(0xffffffffu, lab[r] >= 0 && yk >= 0 && yk < nvalid)) {
                         const int key = (lab[r] >= 0 && yk >= 0 && yk < nvalid) ? lab[r] : -1;
                         const unsigned peers = __match_any_sync(0xffffffffu, key);
                         const unsigned v = key >= 0 ? __float2uint_rn(pyv * kFixI) : 0u;

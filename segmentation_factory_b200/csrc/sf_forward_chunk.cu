@@ -225,7 +225,7 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmap, const FcParams p) {
                             pyv = ex2_approx(__fmaf_rn(zyv, kLog2e, -l2)) * pv;
                             if (DCOEF) py[r] = pyv;
                         }
-                        if (DSTAT) {
+                        if (DSTAT && __any_sync(0xffffffffu, mine)) {      // only the chunk that holds a lane's label class
                             const int key = mine ? lab : -1;
                             const unsigned peers = __match_any_sync(0xffffffffu, key);
                             const unsigned sum = __reduce_add_sync(peers, mine ? __float2uint_rn(pyv * 67108864.f) : 0u);
@@ -233,17 +233,27 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmap, const FcParams p) {
                         }
                     }
                 }
-                if (DSTAT) {                                          // this item's partial sums (<= S pixels per lane) -> shared bins
+                if (DSTAT) {
+                    // this item's partial sums (<= S pixels per lane) -> shared bins.  Transposing butterfly: each step
+                    // halves the values a lane carries while summing over its partner, so 16 classes x 32 lanes take
+                    // 8+4+2+1+1 shuffles (fixed tree => deterministic); lane l ends with class bits (l>>1)&15 reversed below
+                    float v[kFcNCH];
                     #pragma unroll
-                    for (int q = 0; q < NP; ++q) {
+                    for (int q = 0; q < NP; ++q) { v[2 * q] = accp[q].x; v[2 * q + 1] = accp[q].y; }
+                    const int lane = tid & 31;
+                    #pragma unroll
+                    for (int half = kFcNCH / 2, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+                        const bool up = (lane & bit) != 0;
                         #pragma unroll
-                        for (int hh = 0; hh < 2; ++hh) {
-                            const unsigned long long f = __float2ull_rn((hh ? accp[q].y : accp[q].x) * 1099511627776.f);
-                            const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)(f & 0xFFFFFull));
-                            const unsigned hi = __reduce_add_sync(0xffffffffu, (unsigned)(f >> 20));
-                            if (lane_lt == 0 && 2 * q + hh < nvalid) bins.add_sum(c0 + 2 * q + hh, ((unsigned long long)hi << 20) + lo);
+                        for (int i = 0; i < half; ++i) {
+                            const float keep = up ? v[i + half] : v[i];
+                            const float send = up ? v[i] : v[i + half];
+                            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
                         }
                     }
+                    const float tot = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+                    const int cls = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                    if ((lane & 1) == 0 && cls < nvalid) bins.add_sum(c0 + cls, __float2ull_rn(tot * 1099511627776.f));
                 }
                 if (DCOEF && chunk == p.n_chunks - 1 && cnt > 0) {
                     const long long px0 = ((long long)b * p.H + TP::first(u)) * p.W + X;
