@@ -15,6 +15,10 @@ def run(B, C, h, w, H, W, dtype=torch.float32, kind="ohem"):
     loss.backward()
     sf.eval_hist(x.detach(), lab.cuda(), 255, hist)
     f = sf.FocalLoss(0.25, 2.0)(x, lab.cuda()); f.backward()
+    d = sf.criterion(x, lab.cuda(), None, num_classes=C, dice=True, ignore_index=255); d.backward()   # dice walks + backward
+    raw = torch.randint(0, 35, (B, H, W), generator=g, dtype=torch.uint8).cuda()
+    lut = sf.LabelLUT(list(range(19)) + [255] * 16)
+    lut(raw); lut(raw, torch.int64); lut(raw.flatten()[3:-5]); lut(raw.flatten()[1:-2], torch.int64)
     torch.cuda.synchronize()
     print("ok", B, C, h, w, H, W, dtype, kind, float(loss), int(hist.sum()))
 
