@@ -130,24 +130,30 @@ def focal_case(name, seed, B, C, hw, HW, kind, alpha, gamma, size_average, dtype
     print(f"{name:28s} focal={val.item():.6f}")
 
 
-def criterion_case(name, seed, B, C, hw, HW, kind, weighted=False, dice=True, dtype=torch.float32, dead_image=False):
+def criterion_case(name, seed, B, C, hw, HW, kind, weighted=False, dice=True, dtype=torch.float32, dead_image=False,
+                   ignore_index=255, all_ignored=False):
     """engine.criterion (engine.py:10-15): CE + multiclass dice loss through the upsample."""
     from engine import criterion                                                    # the reference's own function
     g = torch.Generator().manual_seed(seed)
     (h, w), (H, W) = hw, HW
-    labels = make_labels(g, B, C, H, W)
+    labels = make_labels(g, B, C, H, W, p_ignore=0.1 if ignore_index == 255 else 0.0)
     if dead_image:
         labels[0].fill_(255)                                                        # empty roi -> sets_sum == 0 branch
+    if all_ignored:
+        labels.fill_(255)
     low = make_logits(g, kind, B, C, h, w, labels).to(dtype)
     cw = torch.rand(C, generator=torch.Generator().manual_seed(7)) + 0.5 if weighted else None
     lowg = low.clone().requires_grad_(True)
     up = F.interpolate(lowg, size=(H, W), mode="bilinear", align_corners=False).float()
-    val = criterion(up, labels, cw, num_classes=C, dice=dice, ignore_index=255)
-    val.backward()
+    val = criterion(up, labels, cw, num_classes=C, dice=dice, ignore_index=ignore_index)
+    if torch.isfinite(val):
+        val.backward()
+    else:
+        lowg.grad = torch.zeros_like(lowg)
     with torch.no_grad():
-        ce = F.cross_entropy(up, labels, ignore_index=255, weight=cw)
+        ce = F.cross_entropy(up, labels, ignore_index=ignore_index, weight=cw)
     np.savez_compressed(os.path.join(OUT, name + ".npz"), logits=bits(low), logits_dtype=str(dtype).replace("torch.", ""),
-                        labels=labels.numpy(), size=np.array([H, W]), dice=np.int32(dice),
+                        labels=labels.numpy(), size=np.array([H, W]), dice=np.int32(dice), ignore_index=np.int32(ignore_index),
                         class_w=(cw.numpy() if weighted else np.zeros(0, np.float32)),
                         loss=np.float32(val.item()), ce=np.float32(ce.item()), grad=lowg.grad.float().numpy())
     print(f"{name:28s} criterion={val.item():.6f} ce={ce.item():.6f}")
@@ -161,6 +167,8 @@ def criterion_cases():
     criterion_case("crit_voc_bf16", 65, 1, 21, (30, 41), (100, 135), "early", dtype=torch.bfloat16)
     criterion_case("crit_dead_image", 66, 2, 19, (16, 32), (64, 128), "early", dead_image=True)
     criterion_case("crit_nodice_weighted", 67, 1, 19, (16, 32), (64, 128), "early", weighted=True, dice=False)
+    criterion_case("crit_default_ignore_m100", 68, 2, 19, (16, 32), (64, 128), "late", ignore_index=-100)   # engine.py:10 default
+    criterion_case("crit_all_ignored", 69, 1, 19, (16, 32), (64, 128), "early", all_ignored=True)            # CE = nan -> nan
 
 
 def label_lut_case():

@@ -94,7 +94,12 @@ def test_criterion_loss_and_gradient(oracle, name):
     """engine.criterion = CE + multiclass dice loss against the reference's own function."""
     g = load_criterion(name)
     dt = DT[g["logits_dtype"]]
-    loss, grad, info = oracle.criterion_loss_and_grad(g["logits"], g["labels"], g["class_w"], bool(g["dice"]), 255, dt)
+    ign = int(g["ignore_index"])
+    loss, grad, info = oracle.criterion_loss_and_grad(g["logits"], g["labels"], g["class_w"], bool(g["dice"]), ign, dt,
+                                                      want_grad=bool(np.isfinite(g["loss"])))
+    if not np.isfinite(g["loss"]):                                   # every pixel ignored: mean over nothing, like the reference
+        assert np.isnan(loss) and np.isnan(g["loss"])
+        return
     assert abs(loss - float(g["loss"])) <= 1e-5 * abs(float(g["loss"])), (loss, float(g["loss"]))
     tol = 1e-5 if g["logits_dtype"] == "float32" else 1e-2
     assert np.abs(grad - g["grad"]).max() <= tol * np.abs(g["grad"]).max(), (np.abs(grad - g["grad"]).max(), np.abs(g["grad"]).max())
