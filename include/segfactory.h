@@ -142,6 +142,13 @@ int sf_dice_stats(const void* logits, int ldtype, const void* labels, int ydtype
                   int B, int C, int h, int w, int H, int W, int ignore,
                   const float* lse_px, void* dice_ws, size_t dice_ws_bytes, void* stream);
 
+/* sf_ce_forward (plain CE, lse_px stored) and sf_dice_stats in one call: a single fused launch where the integer-scale
+ * kernel covers the shape (the exponentials of the log-sum-exp are reused for the softmax sums), else the two launches. */
+int sf_ce_dice_forward(const void* logits, int ldtype, const void* labels, int ydtype,
+                       int B, int C, int h, int w, int H, int W, int ignore,
+                       const float* class_w, float* lse_px, void* workspace, size_t workspace_bytes,
+                       void* dice_ws, size_t dice_ws_bytes, void* stream);
+
 /* D = (2 inter + eps) / (sets + eps), sets == 0 -> sets = 2 inter (util/losses.py:152-155); dice loss = 1 - mean D
  * (:161-177).  Writes sf_dice_state and, when loss_out != NULL, CE + dice to *loss_out (device fp32). */
 int sf_dice_finalize(int B, int C, float epsilon, const void* workspace, void* dice_ws, size_t dice_ws_bytes,

@@ -19,7 +19,7 @@ SF_I64, SF_U8 = 0, 1
 SYMBOLS = (
     "sf_version", "sf_strerror", "sf_workspace_bytes", "sf_eval_hist", "sf_ce_forward",
     "sf_loss_finalize", "sf_focal_finalize", "sf_ce_backward", "sf_hist_pairs", "sf_accumulate_counts",
-    "sf_label_lut", "sf_dice_workspace_bytes", "sf_dice_stats", "sf_dice_finalize", "sf_dice_coef", "sf_dice_backward",
+    "sf_label_lut", "sf_dice_workspace_bytes", "sf_ce_dice_forward", "sf_dice_stats", "sf_dice_finalize", "sf_dice_coef", "sf_dice_backward",
 )
 
 _lib = None
@@ -54,11 +54,12 @@ def lib() -> ctypes.CDLL:
     L.sf_label_lut.restype = i
     L.sf_dice_workspace_bytes.restype = sz
     L.sf_dice_workspace_bytes.argtypes = [i, i]
+    L.sf_ce_dice_forward.argtypes = [vp, i, vp, i, i, i, i, i, i, i, i, vp, vp, vp, sz, vp, sz, vp]
     L.sf_dice_stats.argtypes = [vp, i, vp, i, i, i, i, i, i, i, i, vp, vp, sz, vp]
     L.sf_dice_finalize.argtypes = [i, i, f, vp, vp, sz, vp, vp]
     L.sf_dice_coef.argtypes = [vp, i, vp, i, i, i, i, i, i, i, i, vp, vp, vp, vp, sz, vp, vp, vp]
     L.sf_dice_backward.argtypes = [vp, i, vp, i, i, i, i, i, i, i, i, vp, vp, vp, vp, sz, vp, vp, vp]
-    for name in ("sf_dice_stats", "sf_dice_finalize", "sf_dice_coef", "sf_dice_backward"):
+    for name in ("sf_ce_dice_forward", "sf_dice_stats", "sf_dice_finalize", "sf_dice_coef", "sf_dice_backward"):
         getattr(L, name).restype = i
     for name in ("sf_eval_hist", "sf_ce_forward", "sf_loss_finalize", "sf_focal_finalize", "sf_ce_backward", "sf_hist_pairs", "sf_accumulate_counts"):
         getattr(L, name).restype = i

@@ -147,7 +147,7 @@ static sf::FwdArgs dice_args(const void* logits, int ldtype, const void* labels,
     sf::FwdArgs a{};
     a.logits = logits; a.ldtype = ldtype; a.labels = labels; a.ydtype = ydtype;
     a.B = B; a.C = C; a.h = h; a.w = w; a.H = H; a.W = W; a.ignore = ignore;
-    a.stream = stream; a.softmax = true; a.force_no_tma = sf::env_no_tma();
+    a.stream = stream; a.softmax = false; a.force_no_tma = sf::env_no_tma();
     return a;
 }
 
@@ -157,6 +157,17 @@ int sf_dice_stats(const void* logits, int ldtype, const void* labels, int ydtype
     if (dice_ws_bytes < sf::dice_ws_bytes(B, C)) return SF_ERR_WORKSPACE;
     if ((uintptr_t)dice_ws % 8) return SF_ERR_ALIGN;
     return sf::launch_dice_stats(dice_args(logits, ldtype, labels, ydtype, B, C, h, w, H, W, ignore, stream), lse_px, dice_ws);
+}
+
+int sf_ce_dice_forward(const void* logits, int ldtype, const void* labels, int ydtype, int B, int C, int h, int w, int H,
+                       int W, int ignore, const float* class_w, float* lse_px, void* workspace, size_t workspace_bytes,
+                       void* dice_ws, size_t dice_ws_bytes, void* stream) {
+    if (!workspace || !lse_px || !dice_ws || B <= 0 || C <= 0) return SF_ERR_ARG;
+    if (workspace_bytes < sizeof(sf::Workspace) || dice_ws_bytes < sf::dice_ws_bytes(B, C)) return SF_ERR_WORKSPACE;
+    if ((uintptr_t)dice_ws % 8) return SF_ERR_ALIGN;
+    sf::FwdArgs a = dice_args(logits, ldtype, labels, ydtype, B, C, h, w, H, W, ignore, stream);
+    a.class_w = class_w; a.thresh = -1.0f; a.lse_px = lse_px; a.ws = workspace; a.softmax = true;
+    return sf::launch_ce_dice_forward(a, dice_ws);
 }
 
 int sf_dice_finalize(int B, int C, float epsilon, const void* workspace, void* dice_ws, size_t dice_ws_bytes,

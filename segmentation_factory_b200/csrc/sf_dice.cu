@@ -297,6 +297,31 @@ int launch_dice_stats(const FwdArgs& a, const float* lse_px, void* dice_ws) {
     return launch_dice_walk<DICE_STATS>(a, d);
 }
 
+// CE forward that also gathers the dice sums: one fused launch where the integer-scale kernel covers the shape, else
+// the CE forward followed by the stats walk.
+int launch_ce_dice_forward(const FwdArgs& a, void* dice_ws) {
+    unsigned char* dws = reinterpret_cast<unsigned char*>(dice_ws);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(a.stream);
+    if (!env_no_fast() && (long long)a.H * a.W <= (1LL << 23)) {
+        cudaError_t e = cudaMemsetAsync(dws + kDiceHeaderBytes, 0, (size_t)a.B * a.C * 24, st);
+        if (e != cudaSuccess) return (int)e;
+        FwdArgs f = a;
+        f.softmax = true; f.hist = nullptr; f.loss_px = nullptr;
+        f.dice_mode = DICE_STATS;
+        f.dice = DiceArgs{};
+        f.dice.stats = reinterpret_cast<unsigned long long*>(dws + kDiceHeaderBytes);
+        const int rc = launch_forward_fast(f);                     // FF_SOFTMAX_STATS
+        if (rc != -1000) return rc;
+    }
+    FwdArgs f = a;
+    f.softmax = true; f.dice_mode = DICE_OFF;
+    const int rc = launch_forward(f);
+    if (rc != 0) return rc;
+    FwdArgs g = a;
+    g.softmax = false; g.hist = nullptr; g.loss_px = nullptr; g.lse_px = nullptr;
+    return launch_dice_stats(g, a.lse_px, dice_ws);
+}
+
 int launch_dice_finalize(int B, int C, float eps, const void* ws, void* dice_ws, float* loss_out, void* stream) {
     dice_finalize_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<unsigned char*>(dice_ws), B, C, eps, reinterpret_cast<const Workspace*>(ws), loss_out);

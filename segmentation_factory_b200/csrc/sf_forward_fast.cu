@@ -36,7 +36,7 @@ struct FfParams {
     DiceArgs dice;                                                  // MODE >= 2 (sf_dice.cu)
 };
 
-enum { FF_ARGMAX = 0, FF_SOFTMAX = 1, FF_DICE_STATS = 2, FF_DICE_COEF = 3 };
+enum { FF_ARGMAX = 0, FF_SOFTMAX = 1, FF_DICE_STATS = 2, FF_DICE_COEF = 3, FF_SOFTMAX_STATS = 4 };
 
 template <typename LT, int C, int S>
 struct FfGeom {
@@ -59,8 +59,10 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
     using G = FfGeom<LT, C, S>;
     using TP = ScaleTap<S>;
     constexpr int NP = G::NP;
-    constexpr bool SOFTMAX = MODE == FF_SOFTMAX;
+    constexpr bool CSTAT = MODE == FF_SOFTMAX_STATS;                // CE forward that also gathers the dice sums (criterion)
+    constexpr bool SOFTMAX = MODE == FF_SOFTMAX || CSTAT;
     constexpr bool DSTAT = MODE == FF_DICE_STATS, DCOEF = MODE == FF_DICE_COEF, DICE = DSTAT || DCOEF;
+    constexpr bool ACCP = DSTAT || CSTAT;                           // per-thread sum p_k accumulators + shared bins
     constexpr int CP = C + (C & 1);                                 // even pitch of the per-image dice tables (LDS.64 pairs)
     extern __shared__ __align__(128) unsigned char smem[];
     int* hist_s = reinterpret_cast<int*>(smem + kFfStages * G::STAGE_BYTES);
@@ -71,14 +73,14 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
     const int tid = threadIdx.x;
     const int tx = tid % kFfTW, sy = tid / kFfTW;
     if (tid < 32) cw_s[tid] = (p.class_w && tid < C) ? __ldg(p.class_w + tid) : 1.0f;
-    const bool want_hist = !DICE && p.hist != nullptr;
+    const bool want_hist = !DICE && !CSTAT && p.hist != nullptr;
     const DiceBins bins{reinterpret_cast<unsigned*>(hist_s), C};                        // DSTAT: in the histogram area
     float* tab_s = reinterpret_cast<float*>(full + kFfStages);                          // DCOEF: ta[B][CP], tb[B][CP]
     const int lane = tid & 31;
 
     if (want_hist)
         for (int k = tid; k < C * C; k += kFfThreads) hist_s[k] = 0;
-    if (DSTAT) bins.zero(tid, kFfThreads);
+    if (ACCP) bins.zero(tid, kFfThreads);
     if (DCOEF)
         for (int k = tid; k < 2 * p.B * CP; k += kFfThreads) {
             const int which = k / (p.B * CP), r = k % (p.B * CP), bb = r / CP, cc = r % CP;
@@ -112,10 +114,10 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
     const float2 l2e2 = splat(kLog2e);
 
     // ---- dice state: sum p_k of this thread's roi pixels (DSTAT), flushed as integers so the result is order-free ----
-    float2 accp[(DSTAT && NP > 0) ? NP : 1];
+    float2 accp[(ACCP && NP > 0) ? NP : 1];
     float accpl = 0.f;
     #pragma unroll
-    for (int q = 0; q < ((DSTAT && NP > 0) ? NP : 1); ++q) accp[q] = make_float2(0.f, 0.f);
+    for (int q = 0; q < ((ACCP && NP > 0) ? NP : 1); ++q) accp[q] = make_float2(0.f, 0.f);
     int cur_b = -1, since_flush = 0;
     const float inv_denom = (DCOEF && p.ws) ? p.ws->state.inv_denom : 0.f;
     auto redux3 = [&](float v) -> unsigned long long {               // warp sum of v (<= 2^7) in 2^40 fixed point
@@ -147,7 +149,7 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
         const int b = tile / per_img, rr = tile % per_img;
         const int ua = -1 + (rr / p.tiles_x) * G::NGT;
         const int Xa = (rr % p.tiles_x) * kFfTW;
-        if (DSTAT) {
+        if (ACCP) {
             if (b != cur_b || since_flush >= 8) {                    // keep the fp32 partials short (<= 128 pixels)
                 flush_acc();
                 // a limb word takes <= 8 warps x 16 rows adds per tile
@@ -260,10 +262,15 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
                         const float2 e = __ffma2_rn(z[q], l2e2, nm2);
                         const float2 ex = make_float2(ex2_approx(e.x), ex2_approx(e.y));
                         if (q & 1) b2 = __fadd2_rn(b2, ex); else a2 = __fadd2_rn(a2, ex);
+                        if (CSTAT) z[q] = ex;                        // the exponentials are needed again once the sum is known
                     }
                     a2 = __fadd2_rn(a2, b2);
                     ssum = a2.x + a2.y;
-                    if (G::ODD) ssum += ex2_approx(__fmaf_rn(zl, kLog2e, -m2));
+                    if (G::ODD) {
+                        const float exl = ex2_approx(__fmaf_rn(zl, kLog2e, -m2));
+                        ssum += exl;
+                        if (CSTAT) zl = exl;
+                    }
                 }
                 const bool weird = SOFTMAX ? (ssum != ssum) : (nanflag != nanflag);
                 if (weird) {                                         // torch: NaN beats everything, first NaN wins
@@ -295,6 +302,26 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
                     }
                     if (p.loss_px) p.loss_px[px] = l;
                     if (p.lse_px) p.lse_px[px] = m + lg;
+                }
+                if (CSTAT) {                                         // dice sums: p_k = e_k / sum over the roi pixels
+                    const bool roi = colok && valid;
+                    const float inv = roi ? __fdividef(1.0f, ssum) : 0.f;
+                    const float2 inv2 = splat(inv);
+                    #pragma unroll
+                    for (int q = 0; q < NP; ++q) accp[q] = __ffma2_rn(z[q], inv2, accp[q]);
+                    if (G::ODD) accpl = fmaf(zl, inv, accpl);
+                    float py = 0.f;
+                    if (roi) {
+                        const LT* qk = Sg + lab * G::PLANE;
+                        const float t0 = lerp_pinned(Logit<LT>::ld(qk + o0 + cj0), lw0, Logit<LT>::ld(qk + o0 + cj1), lw1);
+                        const float t1 = lerp_pinned(Logit<LT>::ld(qk + o1 + cj0), lw0, Logit<LT>::ld(qk + o1 + cj1), lw1);
+                        const float zy = Logit<LT>::rnd(lerp_pinned(t0, lh0, t1, lh1));
+                        py = ex2_approx(__fmaf_rn(zy, kLog2e, -m2)) * inv;
+                    }
+                    const int key = roi ? lab : -1;
+                    const unsigned peers = __match_any_sync(0xffffffffu, key);
+                    const unsigned sum = __reduce_add_sync(peers, roi ? __float2uint_rn(py * 67108864.f) : 0u);
+                    if (roi && lane == __ffs(peers) - 1) bins.add_inter(lab, sum, __popc(peers));
                 }
                 if (want_hist) {
                     const int key = (colok && valid) ? lab * C + idx : -1;
@@ -413,7 +440,7 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
         if (tid == 0 && n + kFfStages < n_tiles) issue(n + kFfStages);
     }
 
-    if (DSTAT) {
+    if (ACCP) {
         flush_acc();
         if (cur_b >= 0) flush_bins(cur_b);
     }
@@ -473,6 +500,7 @@ static int ff_launch(const FwdArgs& a) {
 
 template <typename LT, int C, int S>
 static int ff_mode(const FwdArgs& a) {
+    if (a.dice_mode == DICE_STATS && a.softmax) return ff_launch<LT, C, S, FF_SOFTMAX_STATS>(a);   // CE forward + dice sums
     if (a.dice_mode == DICE_STATS) return ff_launch<LT, C, S, FF_DICE_STATS>(a);
     if (a.dice_mode == DICE_COEF) return ff_launch<LT, C, S, FF_DICE_COEF>(a);
     return a.softmax ? ff_launch<LT, C, S, FF_SOFTMAX>(a) : ff_launch<LT, C, S, FF_ARGMAX>(a);

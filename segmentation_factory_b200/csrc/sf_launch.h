@@ -60,6 +60,7 @@ int launch_backward_fast(const BwdArgs& a);   // -1000: shape not covered
 // dice term of engine.criterion (sf_dice.cu)
 size_t dice_ws_bytes(int B, int C);
 int launch_dice_stats(const FwdArgs& a, const float* lse_px, void* dice_ws);
+int launch_ce_dice_forward(const FwdArgs& a, void* dice_ws);   // a: as for sf_ce_forward (lse_px required)
 int launch_dice_finalize(int B, int C, float eps, const void* ws, void* dice_ws, float* loss_out, void* stream);
 int launch_dice_coef(const FwdArgs& a, const float* lse_px, const void* dice_ws, float* coef_a, float* coef_b);
 const float* dice_tb_table(const void* dice_ws, int B, int C);

@@ -181,8 +181,8 @@ def fused_focal_loss(logits, labels, alpha=1.0, gamma=0.0, size_average=True, ig
 
 
 class _FusedCriterion(torch.autograd.Function):
-    """engine.criterion with dice=True: mean CE + multiclass dice loss.  Forward = sf_ce_forward + sf_loss_finalize +
-    sf_dice_stats + sf_dice_finalize (+ sf_dice_coef when a gradient is wanted), backward = sf_dice_backward."""
+    """engine.criterion with dice=True: mean CE + multiclass dice loss.  Forward = sf_ce_dice_forward + sf_loss_finalize +
+    sf_dice_finalize (+ sf_dice_coef when a gradient is wanted), backward = sf_dice_backward."""
 
     @staticmethod
     def forward(ctx, logits, labels, class_w, ignore, eps):
@@ -203,13 +203,11 @@ class _FusedCriterion(torch.autograd.Function):
         with torch.cuda.device(dev):
             st = _stream(dev)
             lc, yc = _LOGIT_CODE[logits.dtype], _LABEL_CODE[labels.dtype]
-            rc = L.sf_ce_forward(_ptr(logits), lc, _ptr(labels), yc, *geo, _ptr(class_w), -1.0,
-                                 None, _ptr(lse_px), None, _ptr(ws), ws_bytes, st)
-            _lib.check(rc, "sf_ce_forward")
+            rc = L.sf_ce_dice_forward(_ptr(logits), lc, _ptr(labels), yc, *geo, _ptr(class_w), _ptr(lse_px),
+                                      _ptr(ws), ws_bytes, _ptr(dws), dws_bytes, st)
+            _lib.check(rc, "sf_ce_dice_forward")
             rc = L.sf_loss_finalize(None, n_px, -1.0, _ptr(ws), ws_bytes, None, st)
             _lib.check(rc, "sf_loss_finalize")
-            rc = L.sf_dice_stats(_ptr(logits), lc, _ptr(labels), yc, *geo, _ptr(lse_px), _ptr(dws), dws_bytes, st)
-            _lib.check(rc, "sf_dice_stats")
             rc = L.sf_dice_finalize(B, C, float(eps), _ptr(ws), _ptr(dws), dws_bytes, _ptr(out), st)
             _lib.check(rc, "sf_dice_finalize")
             if need_grad:

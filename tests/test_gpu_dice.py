@@ -147,7 +147,7 @@ def test_dice_full_size_cityscapes_properties(sf):
     assert 0.0 <= dice <= 1.0
     x = low.cuda().requires_grad_(True)
     loss = sf.criterion(x, lab.cuda(), None, num_classes=C, dice=True, ignore_index=255)
-    assert loss.item() == total
+    assert abs(loss.item() - total) <= 1e-6 * abs(total)       # criterion takes the fused CE + stats forward; _abi_stats the two launches
     loss.backward()
     g = x.grad
     assert torch.isfinite(g).all() and float(g[3].abs().max()) == 0.0
@@ -158,3 +158,32 @@ def test_dice_full_size_cityscapes_properties(sf):
     l2 = sf.criterion(x2, lab.cuda(), None, num_classes=C, dice=False, ignore_index=255)
     l3 = sf.CrossEntropy(255)(low.cuda(), lab.cuda())
     assert l2.item() == l3.item() and abs((total - dice) - l3.item()) <= 1e-5 * abs(l3.item())
+
+
+def test_fused_ce_dice_forward_matches_two_launch_route(sf, oracle):
+    """sf_ce_dice_forward (one launch on integer-scale shapes: the log-sum-exp's exponentials feed the softmax sums) against
+    sf_ce_forward + sf_dice_stats and the oracle."""
+    from segmentation_factory_b200 import _lib
+    L = _lib.lib()
+    for (B, C, h, w, H, W, dt) in [(2, 19, 64, 128, 256, 512, torch.float32), (2, 21, 24, 64, 192, 512, torch.bfloat16),
+                                   (1, 7, 50, 67, 167, 223, torch.float32)]:
+        low, lab = _synth(120, B, C, h, w, H, W, "late", dt, blk=16)
+        stats2, dice2, total2, _, (_, x, y, lse2, ws2, dws2, geo, lc, yc, st) = _abi_stats(low, lab)
+        wsb, dwb = L.sf_workspace_bytes(), L.sf_dice_workspace_bytes(B, C)
+        ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+        dws = torch.empty(dwb, dtype=torch.uint8, device="cuda")
+        lse = torch.empty(B * H * W, dtype=torch.float32, device="cuda")
+        out = torch.empty((), dtype=torch.float32, device="cuda")
+        assert L.sf_ce_dice_forward(x.data_ptr(), lc, y.data_ptr(), yc, *geo, None, lse.data_ptr(), ws.data_ptr(), wsb,
+                                    dws.data_ptr(), dwb, st) == 0
+        assert L.sf_loss_finalize(None, B * H * W, -1.0, ws.data_ptr(), wsb, None, st) == 0
+        assert L.sf_dice_finalize(B, C, 1e-6, ws.data_ptr(), dws.data_ptr(), dwb, out.data_ptr(), st) == 0
+        raw = dws.cpu().numpy()
+        stats = raw[64:64 + B * C * 24].view(np.uint64).reshape(B, C, 3).astype(np.float64)
+        stats[..., 0] /= 2.0 ** 40
+        stats[..., 1] /= 2.0 ** 26
+        assert torch.equal(lse, lse2)                                                     # same lse bits as the plain CE forward
+        assert np.array_equal(stats[..., 2], stats2[..., 2])
+        assert np.abs(stats[..., 0] - stats2[..., 0]).max() <= 2e-6 * stats2[..., 0].max() + 1e-9
+        assert np.abs(stats[..., 1] - stats2[..., 1]).max() <= 2e-6 * max(stats2[..., 1].max(), 1.0)
+        assert abs(out.item() - total2) <= 1e-6 * abs(total2)
