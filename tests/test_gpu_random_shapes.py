@@ -39,10 +39,8 @@ def _case(seed):
     return dict(seed=seed, kind=kind, B=B, C=C, h=h, w=w, H=H, W=W, dtype=dtype, od=od, ldt=ldt, loss=loss, weighted=weighted, late=late)
 
 
-@pytest.mark.parametrize("seed", list(range(48)))
-def test_random_shape(seed, oracle):
-    import segmentation_factory_b200 as sf
-    c = _case(seed)
+def _inputs(c):
+    seed = c["seed"]
     g = torch.Generator().manual_seed(1000 + seed)
     B, C, h, w, H, W = c["B"], c["C"], c["h"], c["w"], c["H"], c["W"]
     blk = 8
@@ -63,6 +61,16 @@ def test_random_shape(seed, oracle):
     lown = low.numpy() if c["dtype"] == torch.float32 else low.view(torch.int16).numpy().view(np.uint16)
     labn = lab.numpy()
     cwn = None if cw is None else cw.numpy()
+
+    return low, lab, cw, lown, labn, cwn
+
+
+@pytest.mark.parametrize("seed", list(range(48)))
+def test_random_shape(seed, oracle):
+    import segmentation_factory_b200 as sf
+    c = _case(seed)
+    B, C, h, w, H, W = c["B"], c["C"], c["h"], c["w"], c["H"], c["W"]
+    low, lab, cw, lown, labn, cwn = _inputs(c)
 
     x = low.cuda().requires_grad_(True)
     y = lab.cuda()
@@ -98,3 +106,23 @@ def test_random_shape(seed, oracle):
         # has the same), not a kernel difference -- the oracle evaluates it in double
         tol = max(tol, 5e-3)
     assert np.abs(got - ref_grad).max() <= tol * scale + 1e-12, (c, np.abs(got - ref_grad).max(), scale)
+
+
+@pytest.mark.parametrize("seed", list(range(100, 132)))
+def test_random_shape_criterion(seed, oracle):
+    """engine.criterion (CE + dice) over the same shape families: fused CE+stats forward, chunked, same-size and generic walks."""
+    import segmentation_factory_b200 as sf
+    c = _case(seed)
+    c["weighted"] = seed % 3 == 0
+    C = c["C"]
+    low, lab, cw, lown, labn, cwn = _inputs(c)
+    x = low.cuda().requires_grad_(True)
+    loss = sf.criterion(x, lab.cuda(), None if cw is None else cw.cuda(), num_classes=C, dice=True, ignore_index=255)
+    loss.backward()
+    ref_loss, ref_grad, _ = oracle.criterion_loss_and_grad(lown, labn, cwn, True, 255, c["od"])
+    assert abs(loss.item() - ref_loss) <= 2e-5 * abs(ref_loss) + 1e-7, (c, loss.item(), ref_loss)
+    got = x.grad.float().cpu().numpy()
+    tol = 2e-5 if c["dtype"] == torch.float32 else 2e-2
+    if c["late"]:
+        tol = max(tol, 1e-4)                                       # same fp32 conditioning note as above
+    assert np.abs(got - ref_grad).max() <= tol * np.abs(ref_grad).max() + 1e-12, (c, np.abs(got - ref_grad).max())
