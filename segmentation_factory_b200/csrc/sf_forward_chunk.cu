@@ -31,7 +31,7 @@ struct FcParams {
     DiceArgs dice;                                                  // MODE >= 2 (sf_dice.cu)
 };
 
-enum { FC_ARGMAX = 0, FC_SOFTMAX = 1, FC_DICE_STATS = 2, FC_DICE_COEF = 3 };
+enum { FC_ARGMAX = 0, FC_SOFTMAX = 1, FC_DICE_STATS = 2, FC_DICE_COEF = 3, FC_SOFTMAX_NOHIST = 4 };
 
 template <typename LT, int S>
 struct FcGeom {
@@ -51,7 +51,8 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmap, const FcParams p) {
     using G = FcGeom<LT, S>;
     using TP = ScaleTap<S>;
     constexpr int NP = kFcNP;
-    constexpr bool SOFTMAX = MODE == FC_SOFTMAX;
+    constexpr bool NOHIST = MODE == FC_SOFTMAX_NOHIST;              // loss only (training without metrics): no argmax index
+    constexpr bool SOFTMAX = MODE == FC_SOFTMAX || NOHIST;
     constexpr bool DSTAT = MODE == FC_DICE_STATS, DCOEF = MODE == FC_DICE_COEF, DICE = DSTAT || DCOEF;
     extern __shared__ __align__(128) unsigned char smem[];
     int* hist_s = reinterpret_cast<int*>(smem + kFcStages * G::STAGE_BYTES);
@@ -61,7 +62,7 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmap, const FcParams p) {
 
     const int tid = threadIdx.x;
     const int tx = tid % kFcTW, sy = tid / kFcTW;
-    const bool want_hist = !DICE && p.hist != nullptr;
+    const bool want_hist = !DICE && !NOHIST && p.hist != nullptr;
     const unsigned lane_lt = (1u << (tid & 31)) - 1u;
     const int C = p.C;
     const int CP = C + (C & 1);                                     // even pitch of the per-image dice tables
@@ -465,6 +466,7 @@ template <typename LT, int S>
 static int fc_mode(const FwdArgs& a) {
     if (a.dice_mode == DICE_STATS) return fc_launch<LT, S, FC_DICE_STATS>(a);
     if (a.dice_mode == DICE_COEF) return fc_launch<LT, S, FC_DICE_COEF>(a);
+    if (a.softmax && !a.hist) return fc_launch<LT, S, FC_SOFTMAX_NOHIST>(a);
     return a.softmax ? fc_launch<LT, S, FC_SOFTMAX>(a) : fc_launch<LT, S, FC_ARGMAX>(a);
 }
 template <typename LT>

@@ -36,7 +36,7 @@ struct FfParams {
     DiceArgs dice;                                                  // MODE >= 2 (sf_dice.cu)
 };
 
-enum { FF_ARGMAX = 0, FF_SOFTMAX = 1, FF_DICE_STATS = 2, FF_DICE_COEF = 3, FF_SOFTMAX_STATS = 4 };
+enum { FF_ARGMAX = 0, FF_SOFTMAX = 1, FF_DICE_STATS = 2, FF_DICE_COEF = 3, FF_SOFTMAX_STATS = 4, FF_SOFTMAX_NOHIST = 5 };
 
 template <typename LT, int C, int S>
 struct FfGeom {
@@ -60,7 +60,8 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
     using TP = ScaleTap<S>;
     constexpr int NP = G::NP;
     constexpr bool CSTAT = MODE == FF_SOFTMAX_STATS;                // CE forward that also gathers the dice sums (criterion)
-    constexpr bool SOFTMAX = MODE == FF_SOFTMAX || CSTAT;
+    constexpr bool NOHIST = MODE == FF_SOFTMAX_NOHIST;              // loss only (training without metrics): no argmax index
+    constexpr bool SOFTMAX = MODE == FF_SOFTMAX || CSTAT || NOHIST;
     constexpr bool DSTAT = MODE == FF_DICE_STATS, DCOEF = MODE == FF_DICE_COEF, DICE = DSTAT || DCOEF;
     constexpr bool ACCP = DSTAT || CSTAT;                           // per-thread sum p_k accumulators + shared bins
     constexpr int CP = C + (C & 1);                                 // even pitch of the per-image dice tables (LDS.64 pairs)
@@ -73,7 +74,7 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
     const int tid = threadIdx.x;
     const int tx = tid % kFfTW, sy = tid / kFfTW;
     if (tid < 32) cw_s[tid] = (p.class_w && tid < C) ? __ldg(p.class_w + tid) : 1.0f;
-    const bool want_hist = !DICE && !CSTAT && p.hist != nullptr;
+    const bool want_hist = !DICE && !CSTAT && !NOHIST && p.hist != nullptr;
     const DiceBins bins{reinterpret_cast<unsigned*>(hist_s), C};                        // DSTAT: in the histogram area
     float* tab_s = reinterpret_cast<float*>(full + kFfStages);                          // DCOEF: ta[B][CP], tb[B][CP]
     const int lane = tid & 31;
@@ -503,6 +504,7 @@ static int ff_mode(const FwdArgs& a) {
     if (a.dice_mode == DICE_STATS && a.softmax) return ff_launch<LT, C, S, FF_SOFTMAX_STATS>(a);   // CE forward + dice sums
     if (a.dice_mode == DICE_STATS) return ff_launch<LT, C, S, FF_DICE_STATS>(a);
     if (a.dice_mode == DICE_COEF) return ff_launch<LT, C, S, FF_DICE_COEF>(a);
+    if (a.softmax && !a.hist) return ff_launch<LT, C, S, FF_SOFTMAX_NOHIST>(a);
     return a.softmax ? ff_launch<LT, C, S, FF_SOFTMAX>(a) : ff_launch<LT, C, S, FF_ARGMAX>(a);
 }
 template <typename LT, int C>
