@@ -58,6 +58,8 @@ DICE_CASES = [
     ("fullres_bf16_c150_u8", 110, 2, 150, 64, 80, 64, 80, "early", torch.bfloat16, torch.uint8, True),
     ("fullres_fp16_late", 112, 3, 21, 96, 128, 96, 128, "late", torch.float16, torch.int64, False),
     ("fullres_fp32_weighted", 113, 2, 19, 128, 160, 128, 160, "late", torch.float32, torch.int64, True),
+    ("fullres_odd_plane", 114, 1, 5, 37, 51, 37, 51, "early", torch.float32, torch.int64, False),     # plane % 4 != 0: generic identity walk
+    ("x2_c24", 115, 1, 24, 40, 64, 80, 128, "late", torch.float32, torch.uint8, False),                # scale 2, C = 24: generic, one chunk
 ]
 
 
