@@ -284,6 +284,7 @@ def main():
         traffic = json.load(open(tp)).get(dom)
     roofline = {"bound": "hbm", "kernel": f"sf::{dom}_fast_kernel<float,19,4>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac_of_hbm3e_spec_8000GBs": achieved / 8000.0,
                 "kernel_ms": kern, "step_frac": algorithmic_bytes_per_px("step") * n_px / (ms_step * 1e-3) / 1e9 / peak,
                 "note": "at C=19 and 1/16 logit density the path is issue/MUFU-bound, not HBM-bound (DESIGN.md)"}
 
