@@ -18,16 +18,25 @@ label_lut_u8_kernel(const uint4* __restrict__ raw, long long n16, const unsigned
     __shared__ unsigned char lut_s[256];
     lut_s[threadIdx.x] = __ldg(lut + threadIdx.x);                  // kLutThreads == 256
     __syncthreads();
-    for (long long i = (long long)blockIdx.x * kLutThreads + threadIdx.x; i < n16; i += (long long)gridDim.x * kLutThreads) {
-        const uint4 v = __ldg(raw + i);
+    auto map16 = [&](const uint4 v) -> uint4 {
         const unsigned w[4] = {v.x, v.y, v.z, v.w};
         unsigned r[4];
         #pragma unroll
         for (int k = 0; k < 4; ++k)
             r[k] = (unsigned)lut_s[w[k] & 0xffu] | ((unsigned)lut_s[(w[k] >> 8) & 0xffu] << 8) |
                    ((unsigned)lut_s[(w[k] >> 16) & 0xffu] << 16) | ((unsigned)lut_s[w[k] >> 24] << 24);
-        out[i] = make_uint4(r[0], r[1], r[2], r[3]);
+        return make_uint4(r[0], r[1], r[2], r[3]);
+    };
+    const long long stride = (long long)gridDim.x * kLutThreads;
+    long long i = (long long)blockIdx.x * kLutThreads + threadIdx.x;
+    for (; i + 3 * stride < n16; i += 4 * stride) {                 // four independent 128-bit loads in flight
+        uint4 v[4];
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = __ldg(raw + i + k * stride);
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) out[i + k * stride] = map16(v[k]);
     }
+    for (; i < n16; i += stride) out[i] = map16(__ldg(raw + i));
 }
 
 // int64 out: the 8 B/px store stream is what matters, so a thread owns 2 pixels = one 16-byte store and a warp's store
