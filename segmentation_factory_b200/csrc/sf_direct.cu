@@ -70,7 +70,6 @@ fwd_direct_kernel(const DirParams p) {
     __shared__ float cw_s[256];
     const int tid = threadIdx.x, C = p.C;
     const bool want_hist = p.hist != nullptr;
-    const unsigned lane_lt = (1u << (tid & 31)) - 1u;
     if (want_hist)
         for (int k = tid; k < C * C; k += kDirThreads) hist_s[k] = 0;
     cw_s[tid] = (p.class_w && tid < C) ? __ldg(p.class_w + tid) : 1.0f;
@@ -79,8 +78,9 @@ fwd_direct_kernel(const DirParams p) {
     const LT* logits = reinterpret_cast<const LT*>(p.logits);
     double acc_loss = 0.0, acc_w = 0.0, acc_hard = 0.0;
     unsigned cnt_valid = 0, cnt_hard = 0;
+    int run_key = -1, run_cnt = 0;
     const long long stride = (long long)gridDim.x * kDirThreads;
-    const long long n_round = (p.n_quads + 31) / 32 * 32;           // whole warps stay in the loop (match_any)
+    const long long n_round = p.n_quads;
 
     for (long long qd = (long long)blockIdx.x * kDirThreads + tid; qd < n_round; qd += stride) {
         const bool live = qd < p.n_quads;
@@ -151,14 +151,18 @@ fwd_direct_kernel(const DirParams p) {
                 if (p.lse_px) p.lse_px[px + v] = m[v] + lg;
             }
             if (want_hist) {
-                const int key = (live && lab[v] >= 0) ? lab[v] * C + idx[v] : -1;
-                const unsigned peers = __match_any_sync(0xffffffffu, key);
-                if (key >= 0 && (peers & lane_lt) == 0) atomicAdd(&hist_s[key], __popc(peers));
+                const int key = (live && lab[v] >= 0) ? lab[v] * C + idx[v] : -1;   // counted as per-thread runs (see sf_forward_fast.cu)
+                if (key != run_key) {
+                    if (run_key >= 0) atomicAdd(&hist_s[run_key], run_cnt);
+                    run_key = key; run_cnt = 0;
+                }
+                ++run_cnt;
             }
         }
     }
 
     if (want_hist) {
+        if (run_key >= 0) atomicAdd(&hist_s[run_key], run_cnt);
         __syncthreads();
         for (int k = tid; k < C * C; k += kDirThreads) {
             const int v = hist_s[k];

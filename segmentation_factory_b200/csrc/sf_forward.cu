@@ -13,8 +13,8 @@
 //     Out-of-image box parts are zero-filled by TMA and never read (indices are clamped like ATen does).
 //   * each thread owns one output column and one row group: per channel 2 FFMA-class ops per pixel for the
 //     vertical lerp, then online softmax state (m, s, argmax) per pixel across channel chunks.
-//   * GT x pred counts go to a shared-memory C x C int32 histogram with warp-aggregated atomics
-//     (__match_any_sync), flushed once per CTA with 64-bit global atomics.
+//   * GT x pred counts go to a shared-memory C x C int32 histogram as per-thread runs (a column's consecutive
+//     pixels mostly share their cell), flushed once per CTA with 64-bit global atomics.
 //   * loss sums are kept per thread in double, reduced per CTA in a fixed order and written to the
 //     workspace (no atomics -> bitwise reproducible loss).
 #include "sf_fwd_generic.cuh"
@@ -57,6 +57,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap, const FwdParams p) {
     // per-thread loss accumulators
     double acc_loss = 0.0, acc_w = 0.0, acc_hard = 0.0;
     unsigned int cnt_valid = 0, cnt_hard = 0;
+    int run_key = -1, run_cnt = 0;
 
     // per-(tile, pass) state
     int X = 0, j0r = 0, j1r = 0, r0 = 0, r1 = 0, nrows = 0, Yb = 0;
@@ -199,9 +200,12 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap, const FwdParams p) {
                         if (p.lse_px) p.lse_px[px] = lse;
                     }
                     if (want_hist) {
-                        const int key = (live && lab[r] >= 0) ? lab[r] * p.C + idx[r] : -1;
-                        const unsigned peers = __match_any_sync(0xffffffffu, key);
-                        if (key >= 0 && (int)(tid & 31) == __ffs(peers) - 1) atomicAdd(&hist_s[key], __popc(peers));
+                        const int key = (live && lab[r] >= 0) ? lab[r] * p.C + idx[r] : -1;   // per-thread runs (see sf_forward_fast.cu)
+                        if (key != run_key) {
+                            if (run_key >= 0) atomicAdd(&hist_s[run_key], run_cnt);
+                            run_key = key; run_cnt = 0;
+                        }
+                        ++run_cnt;
                     }
                 }
             }
@@ -214,6 +218,8 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap, const FwdParams p) {
 
     // ---- CTA epilogue ----
     if (want_hist) {
+        if (run_key >= 0) atomicAdd(&hist_s[run_key], run_cnt);
+        __syncthreads();
         for (int k = tid; k < p.C * p.C; k += kFwdThreads) {
             const int v = hist_s[k];
             if (v) atomicAdd(p.hist + k, (unsigned long long)v);

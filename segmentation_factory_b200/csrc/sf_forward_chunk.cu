@@ -111,6 +111,7 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmap, const FcParams p) {
     double acc_loss = 0.0, acc_w = 0.0, acc_hard = 0.0;
     unsigned int cnt_valid = 0, cnt_hard = 0;
     const float2 l2e2 = splat(kLog2e);
+    int run_key = -1, run_cnt = 0;
 
     // per-(tile) thread state
     int b = 0, ua = 0, X = 0, j0 = 0, j1 = 0, jO = 0, u = 0, cnt = 0, i0 = 0, i1 = 0;
@@ -388,9 +389,12 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmap, const FcParams p) {
                         if (p.lse_px) p.lse_px[px] = m[r] + lg;
                     }
                     if (want_hist) {
-                        const int key = valid ? lab * C + idx[r] : -1;
-                        const unsigned peers = __match_any_sync(0xffffffffu, key);
-                        if (key >= 0 && (peers & lane_lt) == 0) atomicAdd(&hist_s[key], __popc(peers));
+                        const int key = valid ? lab * C + idx[r] : -1;   // per-thread runs (see sf_forward_fast.cu)
+                        if (key != run_key) {
+                            if (run_key >= 0) atomicAdd(&hist_s[run_key], run_cnt);
+                            run_key = key; run_cnt = 0;
+                        }
+                        ++run_cnt;
                     }
                 }
             }
@@ -403,6 +407,8 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmap, const FcParams p) {
 
     if (DSTAT && cur_b >= 0) flush_bins(cur_b);
     if (want_hist) {
+        if (run_key >= 0) atomicAdd(&hist_s[run_key], run_cnt);
+        __syncthreads();
         for (int k = tid; k < C * C; k += kFcThreads) {
             const int v = hist_s[k];
             if (v) atomicAdd(p.hist + k, (unsigned long long)v);
