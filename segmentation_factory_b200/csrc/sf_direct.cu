@@ -7,7 +7,7 @@
 //   * one thread = 4 consecutive pixels, 128-bit loads (fp32) / 64-bit (bf16, fp16) along W for every class plane;
 //   * classes stream in chunks of 8 with an online softmax (running max, rescaled sum, first-max index, label logit);
 //     a NaN logit wins the argmax at its first occurrence, like torch.argmax;
-//   * confusion counts: shared-memory C x C int32, warp-aggregated, one 64-bit flush per CTA;
+//   * confusion counts: shared-memory C x C int32 fed by per-thread runs, one 64-bit flush per CTA;
 //   * backward: g = coef * (2^(z*log2e - lse*log2e) - [c == y]) written straight to grad (overwrites every element).
 #include "sf_common.cuh"
 #include "sf_dice_bins.cuh"
