@@ -132,17 +132,10 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
     // ---- gather role: owned column jl = tid % 64, channels kq, kq+KQ, ...; 2S constant weights ----
     const int jl = tid % kBfJL, kq = tid / kBfJL;
     const bool gat = jl < nown;
-    float wgt[2 * S];
-    {
-        const int j = ja + jl;
-        #pragma unroll
-        for (int d = 0; d < 2 * S; ++d) {
-            float v = d < S ? ((float)d + 0.5f) * (1.0f / S) : 1.0f - ((float)(d - S) + 0.5f) * (1.0f / S);
-            if (j == 0 && d < S) v = d >= S / 2 ? 1.0f : 0.0f;                    // clamped left rim: l0 = 1
-            if (j == p.w - 1 && d >= S) v = d < S + S / 2 ? 1.0f : 0.0f;          // clamped right rim: l0 + l1 = 1
-            wgt[d] = v;
-        }
-    }
+    // The 2S gather weights are constants of S except at the two clamped rims; they are rebuilt inside emit_row from these
+    // two flags instead of living in 2S registers across the row walk (those registers were the kernel's only spills, and
+    // the spill reload's scoreboard slot aliased the row-ahead prefetch: a 14 % long-scoreboard stall inside the channel loop)
+    const bool lrim = ja + jl == 0, rrim = ja + jl == p.w - 1;
     LT* gbase = reinterpret_cast<LT*>(p.grad) + (((long long)b * Ct + c0 + kq) * p.h) * p.w + ja + jl;
 
     const sf_loss_state* stp = &p.ws->state;                        // DICE: never dereferenced (per-pixel weights instead)
@@ -159,24 +152,20 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
     // row loop carries no 64-bit multiplies; `live` counts the rows this column still has to consume.
     int nlo = -1, nhi = -1; float nlse = 0.f, nloss = 0.f, ncb = 0.f;
     const bool has_loss = branch != 0;
-    const long long px0 = ((long long)b * p.H + Ya) * p.W + (colok ? X : 0);
-    const char* lab_p = reinterpret_cast<const char*>(p.labels) + px0 * (p.label_u8 ? 1 : 8);
-    const float* lse_p = p.lse_px + px0;
-    const float* loss_p = (DICE ? p.coef_a : has_loss ? p.loss_px : p.lse_px) + px0;
-    const float* cb_p = (DICE ? p.coef_b : p.lse_px) + px0;
-    const long long lab_step = (long long)p.W * (p.label_u8 ? 1 : 8);
+    // one running pixel offset instead of three or four running pointers (register pressure: see emit_row's note)
+    long long pxo = ((long long)b * p.H + Ya) * p.W + (colok ? X : 0);
+    const float* loss_base = DICE ? p.coef_a : has_loss ? p.loss_px : p.lse_px;
     int to_fetch = colok ? Yb - Ya : 0;
     int live = to_fetch;
     auto prefetch = [&]() {
         if (to_fetch > 0) {
-            if (p.label_u8) { nlo = (int)__ldg(reinterpret_cast<const unsigned char*>(lab_p)); nhi = 0; }
-            else { const int2 t = __ldg(reinterpret_cast<const int2*>(lab_p)); nlo = t.x; nhi = t.y; }
-            nlse = __ldg(lse_p);
-            if (has_loss) nloss = __ldg(loss_p);
-            if (DICE) ncb = __ldg(cb_p);
+            if (p.label_u8) { nlo = (int)__ldg(reinterpret_cast<const unsigned char*>(p.labels) + pxo); nhi = 0; }
+            else { const int2 t = __ldg(reinterpret_cast<const int2*>(p.labels) + pxo); nlo = t.x; nhi = t.y; }
+            nlse = __ldg(p.lse_px + pxo);
+            if (has_loss) nloss = __ldg(loss_base + pxo);
+            if (DICE) ncb = __ldg(p.coef_b + pxo);
         }
-        lab_p += lab_step; lse_p += p.W; loss_p += p.W; --to_fetch;
-        if (DICE) cb_p += p.W;
+        pxo += p.W; --to_fetch;
     };
     prefetch();
     const int ign = p.ignore;
@@ -212,6 +201,14 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
             if (G::ODD) buf[(C - 1) * kBfThreads + tid] = accl;
             __syncthreads();
             if (gat) {
+                float wgt[2 * S];
+                #pragma unroll
+                for (int d = 0; d < 2 * S; ++d) {
+                    float v = d < S ? ((float)d + 0.5f) * (1.0f / S) : 1.0f - ((float)(d - S) + 0.5f) * (1.0f / S);
+                    if (d < S) v = lrim ? (d >= S / 2 ? 1.0f : 0.0f) : v;                 // clamped left rim: l0 = 1
+                    else v = rrim ? (d < S + S / 2 ? 1.0f : 0.0f) : v;                    // clamped right rim: l0 + l1 = 1
+                    wgt[d] = v;
+                }
                 LT* g = gbase + (long long)i * p.w;
                 const float* rk = buf + kq * kBfThreads + S * jl;
                 #pragma unroll
@@ -316,6 +313,16 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
             do_group(u, ta, tal, tb, tbl, accA, accAl, accB, accBl);
             ++u;
         }
+    }
+    {
+        // Touch every staged-row register once, outside the row loops.  ptxas keeps a couple of them in local memory across
+        // the prologue; the reload's scoreboard slot is shared with the row-ahead prefetch loads, so without this the
+        // first reader INSIDE the channel loop waits for that slot on every row (measured: 14 % of all stall samples on
+        // one FMUL2).  Consuming the values here moves that wait out of the loop; the store never happens.
+        float chk = tal + tbl;
+        #pragma unroll
+        for (int q = 0; q < NP; ++q) chk += (ta[q].x + ta[q].y) + (tb[q].x + tb[q].y);
+        if (chk == -1.2345678e38f) *reinterpret_cast<volatile float*>(smem) = chk;
     }
     while (u < ib) {
         do_group(u, ta, tal, tb, tbl, accA, accAl, accB, accBl);
