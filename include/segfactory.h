@@ -13,7 +13,8 @@
  *   - tensors are dense: logits [B,C,h,w] (NCHW), labels [B,H,W]; H,W may differ from h,w, the
  *     bilinear upsample (align_corners=False) of models/build_models.py:65 happens in-kernel;
  *   - return 0 on success, a negative sf_status, or a positive cudaError_t from the launch;
- *   - labels equal to `ignore`, negative, or >= C take no part in loss, gradient or histogram.
+ *   - labels equal to `ignore`, negative, or >= C take no part in loss, gradient or histogram; int64 labels must fit int32
+ *     (the integer-scale kernels read their low 32 bits: every class id, 255, -100 and -1 keep their meaning).
  */
 #ifndef SEGFACTORY_H_
 #define SEGFACTORY_H_

@@ -137,7 +137,6 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
     // two flags instead of living in 2S registers across the row walk (those registers were the kernel's only spills, and
     // the spill reload's scoreboard slot aliased the row-ahead prefetch: a 14 % long-scoreboard stall inside the channel loop)
     const bool lrim = ja + jl == 0, rrim = ja + jl == p.w - 1;
-    LT* gbase = reinterpret_cast<LT*>(p.grad) + (((long long)b * Ct + c0 + kq) * p.h) * p.w + ja + jl;
 
     const sf_loss_state* stp = &p.ws->state;                        // DICE: never dereferenced (per-pixel weights instead)
     const int branch = DICE ? 3 : stp->branch;                      // DICE reads its per-pixel weight like focal does
@@ -149,19 +148,17 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
     // ---- row walk state ----
     const int Ya = TP::first(ia - 1 < -1 ? -1 : ia - 1);
     const int Yb = ib >= p.h ? p.H : TP::first(ib);                // exclusive
-    // Prefetched inputs of the next row (label as two 32-bit halves), fetched through running pointers so the
-    // row loop carries no 64-bit multiplies; `live` counts the rows this column still has to consume.
-    int nlo = -1, nhi = -1; float nlse = 0.f, nloss = 0.f, ncb = 0.f;
+    // Prefetched inputs of the next row, fetched through running pointers so the
+    // row loop carries no 64-bit multiplies; `to_fetch` counts the rows still to fetch (the row being consumed is one behind).
+    int nlo = -1; float nlse = 0.f, nloss = 0.f, ncb = 0.f;
     const bool has_loss = branch != 0;
     // one running pixel offset instead of three or four running pointers (register pressure: see emit_row's note)
     long long pxo = ((long long)b * p.H + Ya) * p.W + (colok ? X : 0);
     const float* loss_base = DICE ? p.coef_a : has_loss ? p.loss_px : p.lse_px;
-    int to_fetch = colok ? Yb - Ya : 0;
-    int live = to_fetch;
+    int to_fetch = colok ? Yb - Ya : 0;                             // rows still to fetch; the row being consumed is one behind
     auto prefetch = [&]() {
         if (to_fetch > 0) {
-            if (p.label_u8) { nlo = (int)__ldg(reinterpret_cast<const unsigned char*>(p.labels) + pxo); nhi = 0; }
-            else { const int2 t = __ldg(reinterpret_cast<const int2*>(p.labels) + pxo); nlo = t.x; nhi = t.y; }
+            nlo = ld_label_lo32(p.labels, p.label_u8, pxo);
             nlse = __ldg(p.lse_px + pxo);
             if (has_loss) nloss = __ldg(loss_base + pxo);
             if (DICE) ncb = __ldg(p.coef_b + pxo);
@@ -219,7 +216,7 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
                     else v = rrim ? (d < S + S / 2 ? 1.0f : 0.0f) : v;                    // clamped right rim: l0 + l1 = 1
                     wgt[d] = v;
                 }
-                LT* g = gbase + (long long)i * p.w;
+                LT* g = reinterpret_cast<LT*>(p.grad) + (((long long)b * Ct + c0 + kq) * p.h + i) * p.w + ja + jl;
                 const float* rk = buf + kq * kBfThreads + S * jl;
                 #pragma unroll
                 for (int k = 0; k < (C + G::KQ - 1) / G::KQ; ++k) {
@@ -253,12 +250,11 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
         const float lh1_step = u < 0 ? 0.0f : inv_s;
         #pragma unroll 1
         for (int r = 0; r < cnt; ++r, lh1 += lh1_step) {
-            const int lo = nlo, hi = nhi; const float lse = nlse, loss = nloss, cbv = ncb;
-            const bool alive = live > 0;
-            --live;
+            const int lo = nlo; const float lse = nlse, loss = nloss, cbv = ncb;
+            const bool alive = to_fetch >= 0;                        // prefetch() runs one row ahead
             prefetch();
-            // valid label: 0 <= y < C, y != ignore (64-bit labels: high word must be zero)
-            const bool valid = alive && hi == 0 && (unsigned)lo < (unsigned)Ct && lo != ign;
+            // valid label: 0 <= y < C, y != ignore (labels are read as their low 32 bits, see ld_label_lo32)
+            const bool valid = alive && (unsigned)lo < (unsigned)Ct && lo != ign;
             float keep = 1.f;
             if (has_loss) keep = is_focal ? loss : (loss > kth ? 1.f : (loss == kth ? tie : 0.f));   // focal: loss_px holds d focal / d ce
             const float wy = cw_s[valid ? lo : 0];

@@ -169,6 +169,12 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
+// log2 of a NORMAL positive float (softmax sums are >= 1): the bare MUFU.LG2, without __log2f's denormal pre/post-scaling
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
@@ -192,6 +198,14 @@ __device__ __forceinline__ float focal_value(float ce, float alpha, float gamma,
 __device__ __forceinline__ long long ld_label(const void* labels, int is_u8, long long idx) {
     return is_u8 ? (long long)__ldg(reinterpret_cast<const unsigned char*>(labels) + idx)
                  : __ldg(reinterpret_cast<const long long*>(labels) + idx);
+}
+
+// Low 32 bits of a label (two's complement).  The integer-scale kernels keep their prefetched labels in one register each:
+// every value in [-2^31, 2^31) -- classes, 255, -100, -1 -- keeps its meaning; labels beyond int32 are outside the contract
+// (the reference would index its bincount out of range with them).
+__device__ __forceinline__ int ld_label_lo32(const void* labels, int is_u8, long long idx) {
+    return is_u8 ? (int)__ldg(reinterpret_cast<const unsigned char*>(labels) + idx)
+                 : __ldg(reinterpret_cast<const int*>(labels) + 2 * idx);
 }
 
 // deterministic block-wide sum of doubles (fixed shuffle tree + fixed warp order); result valid on thread 0

@@ -173,7 +173,7 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
         const int u_first = ua + sy * G::GPS;
         // Labels travel as one byte each (valid classes < C <= 24 here, 255 = not counted), packed 8 per register
         // pair.  Raw 64-bit loads for the NEXT group are issued a whole group ahead and only decoded when needed.
-        long long raw[S];
+        int raw[S];
         float lsn[DICE ? S : 1], lsc[DICE ? S : 1];                  // DICE: the stored lse travels with the labels
         auto fetch_labels = [&](int u) {
             #pragma unroll
@@ -184,7 +184,7 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
                 #pragma unroll
                 for (int r = 0; r < S; ++r)
                     if (r < cnt) {
-                        raw[r] = ld_label(p.labels, p.label_u8, base + (long long)r * p.W);
+                        raw[r] = ld_label_lo32(p.labels, p.label_u8, base + (long long)r * p.W);
                         if (DICE) lsn[r] = __ldg(p.dice.lse_in + base + (long long)r * p.W);
                     }
             }
@@ -194,7 +194,7 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
             #pragma unroll
             for (int r = 0; r < S; ++r) {
                 if (DICE) lsc[r] = lsn[r];
-                const long long y = raw[r];
+                const int y = raw[r];
                 const unsigned v = (y != p.ignore && y >= 0 && y < C) ? (unsigned)y : 255u;
                 pk |= (unsigned long long)v << (8 * r);
             }
@@ -289,7 +289,7 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
                 const bool valid = lab != 255;
                 if (SOFTMAX && colok) {
                     const float corr = __fmaf_rn(m, kLog2e, -m2);          // exact residual of rn(m*log2e)
-                    const float lg = (__log2f(ssum) - corr) * kLn2;
+                    const float lg = (lg2_approx(ssum) - corr) * kLn2;     // ssum >= 1: the max term contributes 2^0
                     float l = 0.f;
                     if (valid) {
                         // label logit: same ops, same bits as the z[] entry of that channel
