@@ -106,7 +106,6 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
     const int b = bid / p.tiles_y;
     const int ia = tyi * kBfTH, ib = min(ia + kBfTH, p.h);
     const int ja = txi * G::TBW, jb = min(ja + G::TBW, p.w);
-    const int nown = jb - ja;
     const int jO = (ja - 1) & ~(G::XAL - 1);                        // box x-origin: 16-byte aligned, -XAL for the first tile
     __shared__ float2 kb_s[DICE ? 12 : 1];                          // DICE: tb[b][c0 + 2q], tb[b][c0 + 2q + 1] (0 past the classes)
     if (DICE && tid < 24) {
@@ -130,14 +129,9 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
     const LT* c1p = Sg + (j1 - jO);
     const float2 lw0_2 = splat(lw0), lw1_2 = splat(lw1);
 
-    // ---- gather role: owned column jl = tid % 64, channels kq, kq+KQ, ...; 2S constant weights ----
-    const int jl = tid % kBfJL, kq = tid / kBfJL;
-    const bool gat = jl < nown;
-    // The 2S gather weights are constants of S except at the two clamped rims; they are rebuilt inside emit_row from these
-    // two flags instead of living in 2S registers across the row walk (those registers were the kernel's only spills, and
-    // the spill reload's scoreboard slot aliased the row-ahead prefetch: a 14 % long-scoreboard stall inside the channel loop)
-    const bool lrim = ja + jl == 0, rrim = ja + jl == p.w - 1;
-
+    // ---- gather role (emit_row): owned column jl = tid % kBfJL, channels kq, kq+KQ, ...  Everything about it is recomputed
+    //      at each emission (8 per tile) instead of living in registers across the row walk: the channel loop needs them
+    //      (ptxas keeps two exp chains in flight only when a few registers are free) ----
     const sf_loss_state* stp = &p.ws->state;                        // DICE: never dereferenced (per-pixel weights instead)
     const int branch = DICE ? 3 : stp->branch;                      // DICE reads its per-pixel weight like focal does
     const float kth = DICE ? 0.f : stp->kth, tie = DICE ? 0.f : stp->tie_share;
@@ -207,7 +201,9 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
             }
             if (G::ODD) buf[(C - 1) * kBfThreads + tid] = accl;
             __syncthreads();
-            if (gat) {
+            const int jl = tid % kBfJL, kq = tid / kBfJL;
+            const bool lrim = ja + jl == 0, rrim = ja + jl == p.w - 1;
+            if (jl < jb - ja) {
                 float wgt[2 * S];
                 #pragma unroll
                 for (int d = 0; d < 2 * S; ++d) {
