@@ -150,20 +150,25 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
     long long pxo = ((long long)b * p.H + Ya) * p.W + (colok ? X : 0);
     const float* loss_base = DICE ? p.coef_a : has_loss ? p.loss_px : p.lse_px;
     int to_fetch = colok ? Yb - Ya : 0;                             // rows still to fetch; the row being consumed is one behind
+    const int lab_shift = p.label_u8 ? 0 : 3;
+    const long long pf_px = (long long)kBfPrefetchRows * p.W;        // L2 prefetch distance in pixels
     auto prefetch = [&]() {
         if (to_fetch > 0) {
-            nlo = ld_label_lo32(p.labels, p.label_u8, pxo);
-            nlse = __ldg(p.lse_px + pxo);
-            if (has_loss) nloss = __ldg(loss_base + pxo);
+            // the prefetch addresses are derived from the load addresses (base + pxo), not recomputed from pxo
+            const char* labp = reinterpret_cast<const char*>(p.labels) + (pxo << lab_shift);
+            const float* lsep = p.lse_px + pxo;
+            const float* lossp = loss_base + pxo;
+            nlo = p.label_u8 ? (int)__ldg(reinterpret_cast<const unsigned char*>(labp)) : __ldg(reinterpret_cast<const int*>(labp));
+            nlse = __ldg(lsep);
+            if (has_loss) nloss = __ldg(lossp);
             if (DICE) ncb = __ldg(p.coef_b + pxo);
             if (to_fetch > kBfPrefetchRows) {
                 // one row of work (~500 clk) does not cover a DRAM miss: measured 14 % long-scoreboard stall on the first use
                 // of these values.  Pull the lines of a few rows ahead into L2 (no registers involved).
-                const long long pf = pxo + (long long)kBfPrefetchRows * p.W;
-                prefetch_l2(reinterpret_cast<const char*>(p.labels) + pf * (p.label_u8 ? 1 : 8));
-                prefetch_l2(p.lse_px + pf);
-                if (has_loss) prefetch_l2(loss_base + pf);
-                if (DICE) prefetch_l2(p.coef_b + pf);
+                prefetch_l2(labp + (pf_px << lab_shift));
+                prefetch_l2(lsep + pf_px);
+                if (has_loss) prefetch_l2(lossp + pf_px);
+                if (DICE) prefetch_l2(p.coef_b + pxo + pf_px);
             }
         }
         pxo += p.W; --to_fetch;
