@@ -123,12 +123,16 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmap, const FcParams p) {
     int idx[S];
     float lse2[DICE ? S : 1], pcf[DICE ? S : 1], Gs[DICE ? S : 1], py[DICE ? S : 1];
 
+    // (tile, chunk) and the ring slot advance as counters: a division by the runtime chunk count per item and thread was
+    // ~20 instructions (IABS / MUFU.RCP / ...) in a loop body of ~200
+    int chunk = -1, tile_i = -1, slot = -1, phase = 1;
     for (int n = 0; n < n_items; ++n) {
-        const int chunk = n % p.n_chunks;
-        const LT* Sg = reinterpret_cast<const LT*>(smem + (n % kFcStages) * G::STAGE_BYTES);
+        if (++chunk == p.n_chunks || n == 0) { chunk = 0; ++tile_i; }
+        if (++slot == kFcStages || n == 0) { slot = 0; phase ^= 1; }
+        const LT* Sg = reinterpret_cast<const LT*>(smem + slot * G::STAGE_BYTES);
 
         if (chunk == 0) {
-            const int tile = blockIdx.x + (n / p.n_chunks) * gridDim.x;
+            const int tile = blockIdx.x + tile_i * gridDim.x;
             b = tile / per_img;
             if (DSTAT) {                                             // a limb word takes <= 16 warps x S rows adds per tile
                 if (cur_b >= 0 && (b != cur_b || tiles_in_bins >= kDiceFlushAdds / (16 * S))) { flush_bins(cur_b); tiles_in_bins = 0; }
@@ -169,7 +173,7 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmap, const FcParams p) {
             }
         }
 
-        mbar_wait(&full[n % kFcStages], (uint32_t)((n / kFcStages) & 1));
+        mbar_wait(&full[slot], (uint32_t)phase);
 
         if (DICE) {
             // warp-uniform guard (a warp shares sy): the reductions below need every lane, idle columns carry no valid pixel
