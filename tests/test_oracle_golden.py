@@ -103,3 +103,26 @@ def test_criterion_loss_and_gradient(oracle, name):
     assert abs(loss - float(g["loss"])) <= 1e-5 * abs(float(g["loss"])), (loss, float(g["loss"]))
     tol = 1e-5 if g["logits_dtype"] == "float32" else 1e-2
     assert np.abs(grad - g["grad"]).max() <= tol * np.abs(g["grad"]).max(), (np.abs(grad - g["grad"]).max(), np.abs(g["grad"]).max())
+
+
+def test_criterion_oracle_gradient_is_the_derivative_of_its_loss(oracle):
+    """Independent of the goldens: central differences of the oracle's own criterion value reproduce its analytic gradient
+    (dice through softmax and the transposed bilinear resize), including a class that is absent from one image."""
+    rng = np.random.default_rng(7)
+    B, C, h, w, H, W = 2, 4, 5, 6, 11, 13
+    low = rng.normal(0, 2, (B, C, h, w)).astype(np.float32)
+    lab = rng.integers(0, C, (B, H, W)).astype(np.int64)
+    lab[0][lab[0] == 3] = 1                      # class 3 absent in image 0
+    lab[1, :3, :] = 255
+    cw = (rng.random(C) + 0.5).astype(np.float32)
+    _, grad, _ = oracle.criterion_loss_and_grad(low, lab, cw, True, 255)
+    eps = 1e-2
+    for _ in range(12):
+        idx = tuple(int(rng.integers(0, n)) for n in low.shape)
+        lp, lm = low.copy(), low.copy()
+        lp[idx] += eps
+        lm[idx] -= eps
+        fp, _, _ = oracle.criterion_loss_and_grad(lp, lab, cw, True, 255, want_grad=False)
+        fm, _, _ = oracle.criterion_loss_and_grad(lm, lab, cw, True, 255, want_grad=False)
+        fd = (fp - fm) / (float(lp[idx]) - float(lm[idx]))
+        assert abs(fd - grad[idx]) <= 2e-3 * max(abs(grad[idx]), 1e-3) + 2e-5, (idx, fd, grad[idx])
