@@ -69,6 +69,7 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
     int* hist_s = reinterpret_cast<int*>(smem + kFfStages * G::STAGE_BYTES);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + kFfStages * G::STAGE_BYTES + round_up(C * C * 4, 16));
     __shared__ double red_scratch[kFfThreads / 32];
+    __shared__ uint64_t empty_bar[kFfStages];                       // consumer -> producer: "every warp is done with this stage"
     __shared__ float cw_s[32];                                      // class weights as LDS: an LDG in the row loop would share
                                                                     // a scoreboard slot with the label prefetch and serialise it
     const int tid = threadIdx.x;
@@ -89,7 +90,7 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
         }
     if (tid == 0) {
         tma_prefetch_desc(&tmap);
-        for (int s = 0; s < kFfStages; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < kFfStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty_bar[s], kFfThreads / 32); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -444,8 +445,15 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
         }
         acc_loss += (double)tile_loss; acc_w += (double)tile_w; acc_hard += (double)tile_hard;
 
-        __syncthreads();                                             // all threads are done with this stage
-        if (tid == 0 && n + kFfStages < n_tiles) issue(n + kFfStages);
+        // Release the stage warp by warp instead of a CTA-wide barrier per tile (measured: 4.5 % of the stall samples): only
+        // the producer thread waits until all 8 warps have left the tile before its TMA overwrites the stage; the other
+        // warps run ahead into the next tile, whose stage landed a tile ago.
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[n % kFfStages]);
+        if (tid == 0 && n + kFfStages < n_tiles) {
+            mbar_wait(&empty_bar[n % kFfStages], (uint32_t)((n / kFfStages) & 1));
+            issue(n + kFfStages);
+        }
     }
 
     if (ACCP) {
