@@ -29,6 +29,7 @@ class Metrics:
         self.hist = torch.zeros(num_classes, num_classes).to(device)
         self.hist_i64 = torch.zeros(num_classes, num_classes, dtype=torch.int64).to(device)
         self.device = device
+        self.pq_hist = {"TP": 0, "FP": 0, "FN": 0, "iou_sum": 0.0}   # util/metrics.py:17-22: kept for attribute parity only
         self._counts = None               # per-call matrix (device scratch, left zeroed by sf_accumulate_counts)
 
     def _accumulate(self, counts: Tensor) -> None:
@@ -41,6 +42,20 @@ class Metrics:
         counts = self._scratch(pred.device)
         eval_hist(pred, target, self.ignore_label, counts, size)
         accumulate_counts(counts, self.hist, self.hist_i64, None)
+
+    def update_pq(self, gt_masks, pred_masks, iou_threshold=0.5):
+        """util/metrics.py:50-91 (instance-mask matching for panoptic quality).  Nothing in the reference calls it and it is not
+        part of the per-pixel head-to-metric path this package implements (out of scope)."""
+        raise NotImplementedError("Metrics.update_pq is outside the per-pixel head-to-metric path of segmentation_factory_b200; "
+                                  "use the reference's util.metrics.Metrics for instance / panoptic quality")
+
+    def compute_pq(self):
+        """util/metrics.py:94-106 on whatever `pq_hist` holds (pure host arithmetic)."""
+        tp, fp, fn, iou_sum = (self.pq_hist[k] for k in ("TP", "FP", "FN", "iou_sum"))
+        sq = iou_sum / tp if tp > 0 else 0.0
+        den = tp + 0.5 * fp + 0.5 * fn
+        rq = tp / den if den > 0 else 0.0
+        return round(sq * rq * 100, 2), round(sq * 100, 2), round(rq * 100, 2)
 
     def _scratch(self, device):
         if self._counts is None or self._counts.device != device:

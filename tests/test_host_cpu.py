@@ -123,3 +123,14 @@ def test_label_lut_table_matches_reference_encoders():
         sf.LabelLUT(z["cs_table"], device="cpu")(torch.zeros(4, dtype=torch.int64))
     with pytest.raises(ValueError):
         sf.LabelLUT(np.arange(300))
+
+
+def test_metrics_pq_surface():
+    """Attribute parity with util/metrics.py: pq_hist exists, compute_pq is the reference's formula, update_pq says why it is absent."""
+    import segmentation_factory_b200 as sf
+    m = sf.Metrics(3, 255, "cpu")
+    assert m.compute_pq() == (0.0, 0.0, 0.0)
+    m.pq_hist.update(TP=3, FP=1, FN=2, iou_sum=2.4)
+    assert m.compute_pq() == (round(0.8 * (3 / 4.5) * 100, 2), 80.0, round(3 / 4.5 * 100, 2))
+    with pytest.raises(NotImplementedError):
+        m.update_pq([], [])
