@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SF_VERSION 101            /* 0.1.1 */
+#define SF_VERSION 200            /* 0.2.0 */
 
 enum sf_dtype       { SF_F32 = 0, SF_BF16 = 1, SF_F16 = 2 };     /* logits / gradient element type */
 enum sf_label_dtype { SF_I64 = 0, SF_U8 = 1 };                   /* datasets/*.py: int64, Kvasir uint8 */
@@ -38,7 +38,9 @@ enum sf_status {
     SF_ERR_TOO_MANY_CLASSES = -3,/* C*C int32 histogram does not fit in shared memory (C > 230) */
     SF_ERR_WORKSPACE   = -4,     /* workspace smaller than sf_workspace_bytes()                */
     SF_ERR_DRIVER      = -5,     /* cuTensorMapEncodeTiled unavailable / failed                */
-    SF_ERR_SHAPE       = -6      /* extents overflow the kernels' 32-bit tile arithmetic       */
+    SF_ERR_SHAPE       = -6,     /* extents overflow the kernels' 32-bit tile arithmetic       */
+    SF_ERR_UNSUPPORTED = -7      /* sf_ce_onepass: shape outside the one-pass kernels -- use
+                                    sf_ce_forward / sf_loss_finalize / sf_ce_backward instead     */
 };
 
 /* Device-resident result of sf_loss_finalize (first bytes of the workspace). */
@@ -119,6 +121,38 @@ int sf_ce_backward(const void* logits, int ldtype, const void* labels, int ydtyp
                    const float* class_w, const float* loss_px, const float* lse_px,
                    const float* grad_out, const void* workspace,
                    void* grad_logits, void* stream);
+
+/*
+ * One-pass form of sf_ce_forward + sf_ce_backward for training steps (util/losses.py:32-36, 52-57 + autograd): ONE walk
+ * over the label pixels computes the per-pixel loss, the confusion counts AND the softmax-minus-onehot gradient, because
+ * the keep rule of plain CE (label != ignore) and of the OHEM threshold branch (loss > thresh) is pixel-local; only the
+ * 1/sum(w) or 1/K scale is global and is applied by sf_ce_onepass_backward.  Call order for one step:
+ *   sf_ce_onepass -> sf_loss_finalize -> [sf_ce_onepass_backward when the gradient is wanted].
+ *   loss_px   [B*H*W] fp32, required when ohem_thresh >= 0 (the top-k fallback selects from it), else nullable
+ *   hist      [C*C] accumulated, nullable
+ *   grad_acc  [B*C*h*w] fp32 scratch: unscaled gradient sums, overwritten
+ * Returns SF_ERR_UNSUPPORTED for shapes outside the one-pass kernels (H == S*h, W == S*w, S in {4, 8}, C in {19, 21},
+ * 16-byte aligned rows); sf_ce_onepass_supported() tells beforehand.  Nothing is launched in that case.
+ */
+int sf_ce_onepass_supported(int ldtype, const void* logits, int C, int h, int w, int H, int W);
+int sf_ce_onepass(const void* logits, int ldtype, const void* labels, int ydtype,
+                  int B, int C, int h, int w, int H, int W, int ignore,
+                  const float* class_w, float ohem_thresh,
+                  float* loss_px, unsigned long long* hist, float* grad_acc,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Completes the backward of sf_ce_onepass after sf_loss_finalize, without host synchronisation:
+ *   branch 0 / 1 (CE, OHEM threshold): grad_logits = grad_acc * grad_out / denom (one streaming kernel);
+ *   branch 2 (OHEM top-k fallback, util/losses.py:58-59): the speculative sums are void -- a second walk keeps the pixels
+ *   with loss_px > k-th value (ties share, see sf_loss_state) and writes grad_logits directly.
+ * Both kernels are always launched; each exits at once when the device-side branch is not its own.
+ */
+int sf_ce_onepass_backward(const void* logits, int ldtype, const void* labels, int ydtype,
+                           int B, int C, int h, int w, int H, int W, int ignore,
+                           const float* class_w, const float* loss_px, const float* grad_acc,
+                           const float* grad_out, const void* workspace,
+                           void* grad_logits, void* stream);
 
 /*
  * Dice term of engine.criterion (engine.py:10-15: loss = F.cross_entropy(...) + dice_loss(softmax(x), build_target(...),

@@ -46,6 +46,8 @@ def lib():
         L.orc_dice_stats.argtypes = [vp, i, vp, i, i, i, i, i, i, i, i, vp, vp]
         L.orc_dice_backward.argtypes = [vp, i, vp, i, i, i, i, i, i, i, i, vp, vp, ctypes.c_double, vp, vp, vp]
         L.orc_num_threads.restype = i
+        L.orc_set_num_threads.argtypes = [i]
+        L.orc_set_num_threads.restype = None
         _lib = L
     return _lib
 
@@ -74,6 +76,11 @@ def labels_code(labels: np.ndarray) -> int:
 
 def num_threads() -> int:
     return lib().orc_num_threads()
+
+
+def set_num_threads(n: int) -> None:
+    """Override OMP_NUM_THREADS (torch.distributed.run sets it to 1 for its workers)."""
+    lib().orc_set_num_threads(int(n))
 
 
 def upsample(logits: np.ndarray, size, ldtype: int | None = None) -> np.ndarray:

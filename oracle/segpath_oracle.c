@@ -411,3 +411,13 @@ int orc_num_threads(void) {
     return 1;
 #endif
 }
+
+/* Benchmark helper: torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; the CPU baseline must still use every
+ * host core it is given. */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}

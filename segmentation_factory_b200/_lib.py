@@ -15,11 +15,11 @@ LIB_PATH = os.path.join(_HERE, "libsegfactory.so")
 SF_F32, SF_BF16, SF_F16 = 0, 1, 2
 SF_I64, SF_U8 = 0, 1
 
-# every symbol include/segfactory.h declares (tests/test_abi_symbols.py checks the .so exports them)
+# every symbol include/segfactory.h declares (tests/test_host_cpu.py checks the .so exports them)
 SYMBOLS = (
     "sf_version", "sf_strerror", "sf_workspace_bytes", "sf_eval_hist", "sf_ce_forward",
     "sf_loss_finalize", "sf_focal_finalize", "sf_ce_backward", "sf_hist_pairs", "sf_accumulate_counts",
-    "sf_label_lut", "sf_dice_workspace_bytes", "sf_ce_dice_forward", "sf_dice_stats", "sf_dice_finalize", "sf_dice_coef", "sf_dice_backward",
+    "sf_label_lut", "sf_ce_onepass_supported", "sf_ce_onepass", "sf_ce_onepass_backward", "sf_dice_workspace_bytes", "sf_ce_dice_forward", "sf_dice_stats", "sf_dice_finalize", "sf_dice_coef", "sf_dice_backward",
 )
 
 _lib = None
@@ -48,6 +48,11 @@ def lib() -> ctypes.CDLL:
     L.sf_loss_finalize.argtypes = [vp, ll, f, vp, sz, vp, vp]
     L.sf_focal_finalize.argtypes = [vp, ll, f, f, i, vp, sz, vp, vp]
     L.sf_ce_backward.argtypes = [vp, i, vp, i, i, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp]
+    L.sf_ce_onepass_supported.argtypes = [i, vp, i, i, i, i, i]
+    L.sf_ce_onepass.argtypes = [vp, i, vp, i, i, i, i, i, i, i, i, vp, f, vp, vp, vp, vp, sz, vp]
+    L.sf_ce_onepass_backward.argtypes = [vp, i, vp, i, i, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp]
+    for name in ("sf_ce_onepass_supported", "sf_ce_onepass", "sf_ce_onepass_backward"):
+        getattr(L, name).restype = i
     L.sf_hist_pairs.argtypes = [vp, i, vp, ll, i, vp, vp]
     L.sf_accumulate_counts.argtypes = [vp, vp, vp, vp, i, vp]
     L.sf_label_lut.argtypes = [vp, ll, vp, vp, i, vp]

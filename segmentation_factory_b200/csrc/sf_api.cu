@@ -83,6 +83,7 @@ const char* sf_strerror(int code) {
         case SF_ERR_WORKSPACE: return "workspace smaller than sf_workspace_bytes()";
         case SF_ERR_DRIVER: return "cuTensorMapEncodeTiled unavailable or failed";
         case SF_ERR_SHAPE: return "extents overflow the kernels' tile arithmetic";
+        case SF_ERR_UNSUPPORTED: return "shape outside the one-pass kernels (use sf_ce_forward / sf_ce_backward)";
         default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "unknown segfactory error";
     }
 }
@@ -138,6 +139,53 @@ int sf_ce_backward(const void* logits, int ldtype, const void* labels, int ydtyp
     a.class_w = class_w; a.loss_px = loss_px; a.lse_px = lse_px; a.grad_out = grad_out; a.ws = workspace;
     a.grad_logits = grad_logits; a.stream = stream; a.force_no_tma = sf::env_no_tma();
     return sf::launch_backward(a);
+}
+
+int sf_ce_onepass_supported(int ldtype, const void* logits, int C, int h, int w, int H, int W) {
+    return sf::onepass_supported(ldtype, logits, C, h, w, H, W) ? 1 : 0;
+}
+
+static int onepass_check(const void* logits, int ldtype, const void* labels, int ydtype, int B, int C, int h, int w, int H,
+                         int W) {
+    if (!logits || !labels || B <= 0 || C <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0) return SF_ERR_ARG;
+    if (ldtype < SF_F32 || ldtype > SF_F16 || ydtype < SF_I64 || ydtype > SF_U8) return SF_ERR_ARG;
+    if (ydtype == SF_I64 && ((uintptr_t)labels % 8)) return SF_ERR_ALIGN;
+    if ((long long)B * H * W >= (1LL << 40) || (long long)B * C >= (1LL << 31)) return SF_ERR_SHAPE;
+    return SF_OK;
+}
+
+int sf_ce_onepass(const void* logits, int ldtype, const void* labels, int ydtype, int B, int C, int h, int w, int H,
+                  int W, int ignore, const float* class_w, float ohem_thresh, float* loss_px, unsigned long long* hist,
+                  float* grad_acc, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!workspace || !grad_acc) return SF_ERR_ARG;
+    if (workspace_bytes < sizeof(sf::Workspace)) return SF_ERR_WORKSPACE;
+    if (ohem_thresh >= 0.f && !loss_px) return SF_ERR_ARG;          // the top-k fallback needs the loss vector
+    const int rc = onepass_check(logits, ldtype, labels, ydtype, B, C, h, w, H, W);
+    if (rc != SF_OK) return rc;
+    sf::OnepassArgs a{};
+    a.logits = logits; a.ldtype = ldtype; a.labels = labels; a.ydtype = ydtype;
+    a.B = B; a.C = C; a.h = h; a.w = w; a.H = H; a.W = W; a.ignore = ignore;
+    a.class_w = class_w; a.thresh = ohem_thresh; a.loss_px = loss_px; a.hist = hist; a.grad_acc = grad_acc;
+    a.ws = workspace; a.stream = stream; a.mode = 0;
+    return sf::launch_onepass(a);
+}
+
+int sf_ce_onepass_backward(const void* logits, int ldtype, const void* labels, int ydtype, int B, int C, int h, int w,
+                           int H, int W, int ignore, const float* class_w, const float* loss_px, const float* grad_acc,
+                           const float* grad_out, const void* workspace, void* grad_logits, void* stream) {
+    if (!workspace || !grad_acc || !grad_logits) return SF_ERR_ARG;
+    int rc = onepass_check(logits, ldtype, labels, ydtype, B, C, h, w, H, W);
+    if (rc != SF_OK) return rc;
+    if (loss_px) {                                                   // plain CE keeps no loss vector and has no top-k branch
+        sf::OnepassArgs a{};
+        a.logits = logits; a.ldtype = ldtype; a.labels = labels; a.ydtype = ydtype;
+        a.B = B; a.C = C; a.h = h; a.w = w; a.H = H; a.W = W; a.ignore = ignore;
+        a.class_w = class_w; a.thresh = 0.f; a.loss_px = const_cast<float*>(loss_px); a.grad_out = grad_out;
+        a.grad_logits = grad_logits; a.ws = const_cast<void*>(workspace); a.stream = stream; a.mode = 1; a.only_branch2 = 1;
+        rc = sf::launch_onepass(a);
+        if (rc != SF_OK) return rc;
+    }
+    return sf::launch_onepass_scale(grad_acc, grad_logits, ldtype, (long long)B * C * h * w, grad_out, workspace, stream);
 }
 
 size_t sf_dice_workspace_bytes(int B, int C) { return (B > 0 && C > 0) ? sf::dice_ws_bytes(B, C) : 0; }

@@ -35,7 +35,16 @@ struct Workspace {
     double        partials[kMaxCtas][kPartialStride];  // {sum_loss, sum_w, sum_hard, n_valid, n_hard}
     double        sel_partials[kMaxCtas];              // pass-D partial sums of the radix select
     unsigned int  radix_hist[3][kRadixBins];
+    // Order-free totals of the one-pass kernel (sf_onepass.cu): its grid is one CTA per tile (thousands), so instead of
+    // per-CTA slots every CTA adds its partial sums as 128-bit fixed point (2^-40 units, two's complement, {lo, hi}) with
+    // integer atomics -- integer addition is associative, so the loss stays bitwise reproducible.  n_partials == kFxMarker
+    // tells sf_loss_finalize to read these instead of `partials`.
+    unsigned long long fx_loss[2], fx_w[2], fx_hard[2];
+    unsigned long long fx_n_valid, fx_n_hard;
+    unsigned int  fx_flags;                            // non-finite partials: 3 bits (nan, +inf, -inf) per sum
+    unsigned int  pad1[3];
 };
+constexpr unsigned int kFxMarker = 0xFFFFFFFFu;
 
 // ---------------------------------------------------------------------------------------------
 // Logit element traits: load-as-float, round-to-dtype, store
@@ -209,6 +218,26 @@ __device__ __forceinline__ long long ld_label(const void* labels, int is_u8, lon
 __device__ __forceinline__ int ld_label_lo32(const void* labels, int is_u8, long long idx) {
     return is_u8 ? (int)__ldg(reinterpret_cast<const unsigned char*>(labels) + idx)
                  : __ldg(reinterpret_cast<const int*>(labels) + 2 * idx);
+}
+
+// 128-bit fixed-point accumulation of a double (see Workspace::fx_*).  |v| < 2^87; quantum 2^-40 per call.
+__device__ __forceinline__ void fx_add(unsigned long long* acc, unsigned int* flags, int which, double v) {
+    if (!isfinite(v)) { atomicOr(flags, (isnan(v) ? 1u : v > 0 ? 2u : 4u) << (3 * which)); return; }
+    const double s = v * 0x1p40;
+    const double h = floor(s * 0x1p-64);
+    const double l = s - h * 0x1p64;                                // exact, in [0, 2^64)
+    const unsigned long long lo = __double2ull_rz(l);
+    long long hi = __double2ll_rz(h);
+    const unsigned long long old = atomicAdd(&acc[0], lo);
+    if (old + lo < old) ++hi;                                       // carry out of the low word
+    if (hi) atomicAdd(&acc[1], (unsigned long long)hi);
+}
+__device__ __forceinline__ double fx_get(const unsigned long long* acc, unsigned int flags, int which) {
+    const unsigned int f = (flags >> (3 * which)) & 7u;
+    if (f) return (f & 1u) || ((f & 2u) && (f & 4u)) ? __longlong_as_double(0x7ff8000000000000LL)
+                                                     : (f & 2u) ? __longlong_as_double(0x7ff0000000000000LL)
+                                                                : __longlong_as_double(0xfff0000000000000LL);
+    return (double)(long long)__ldcg(&acc[1]) * 0x1p24 + (double)__ldcg(&acc[0]) * 0x1p-40;
 }
 
 // deterministic block-wide sum of doubles (fixed shuffle tree + fixed warp order); result valid on thread 0

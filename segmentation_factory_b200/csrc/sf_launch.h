@@ -57,6 +57,28 @@ int launch_backward(const BwdArgs& a);
 int launch_backward_direct(const BwdArgs& a);
 int launch_backward_fast(const BwdArgs& a);   // -1000: shape not covered
 
+// One-pass forward + backward (sf_onepass.cu): integer-scale heads with C <= 24.
+struct OnepassArgs {
+    const void* logits; int ldtype;
+    const void* labels; int ydtype;
+    int B, C, h, w, H, W, ignore;
+    const float* class_w;
+    float thresh;                  // < 0: plain CE
+    float* loss_px;                // fused walk: written (required under OHEM); backward walk: read
+    unsigned long long* hist;      // fused walk only, nullable
+    float* grad_acc;               // fused walk: [B,C,h,w] fp32, unscaled (softmax - onehot) * keep * w_y sums
+    const float* grad_out;         // backward walk
+    void* grad_logits;             // backward walk: [B,C,h,w] in the logits' dtype, final
+    void* ws;
+    void* stream;
+    int mode;                      // 0 = fused walk, 1 = backward walk (top-k fallback)
+    int only_branch2;              // backward walk: no-op unless sf_loss_state.branch == 2
+};
+bool onepass_supported(int ldtype, const void* logits, int C, int h, int w, int H, int W);
+int launch_onepass(const OnepassArgs& a);      // SF_ERR_UNSUPPORTED: shape not covered
+int launch_onepass_scale(const float* acc, void* out, int ldtype, long long n, const float* grad_out, const void* ws,
+                         void* stream);
+
 // dice term of engine.criterion (sf_dice.cu)
 size_t dice_ws_bytes(int B, int C);
 int launch_dice_stats(const FwdArgs& a, const float* lse_px, void* dice_ws);

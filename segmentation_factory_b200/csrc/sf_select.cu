@@ -119,7 +119,14 @@ finalize_kernel(const float* __restrict__ loss_px, long long n, float thresh, Wo
 
     // ---- phase 0: fixed-order reduction of the forward kernel's per-CTA partials (all five sums behind one barrier
     //      pair: this prologue is the whole kernel on the CE / threshold branches) ----
-    {
+    if (ws->n_partials == kFxMarker) {                              // one-pass kernel: order-free fixed-point totals
+        if (threadIdx.x == 0) {
+            const unsigned int fl = __ldcg(&ws->fx_flags);
+            tot[0] = fx_get(ws->fx_loss, fl, 0); tot[1] = fx_get(ws->fx_w, fl, 1); tot[2] = fx_get(ws->fx_hard, fl, 2);
+            tot[3] = (double)__ldcg(&ws->fx_n_valid); tot[4] = (double)__ldcg(&ws->fx_n_hard);
+        }
+        __syncthreads();
+    } else {
         const int np = (int)ws->n_partials;
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         const int nw = (np + 31) / 32;                              // warps that hold partials (<= 32)

@@ -6,8 +6,10 @@ happens in libsegfactory.so.  Nothing here synchronises with the host.
 from __future__ import annotations
 
 import math
+import os
 
 import torch
+from torch.autograd.function import once_differentiable
 
 from . import _lib
 
@@ -75,6 +77,16 @@ def eval_hist(logits: torch.Tensor, labels: torch.Tensor, ignore: int, hist: tor
     _lib.check(rc, "sf_eval_hist")
 
 
+def _check_cells(name, t, dtype, like) -> None:
+    """A raw pointer is about to be handed to a kernel: a host tensor, a tensor on another GPU, a strided view or a
+    wrong dtype would be an illegal address (sticky context error) instead of a Python exception."""
+    if t is None:
+        return
+    if not t.is_cuda or t.device != like.device or t.dtype != dtype or not t.is_contiguous() or t.numel() != like.numel():
+        raise ValueError(f"{name} must be a contiguous {dtype} tensor with {like.numel()} cells on {like.device} "
+                         f"(got {t.dtype}, {tuple(t.shape)}, {t.device})")
+
+
 def hist_pairs(a: torch.Tensor, b: torch.Tensor, C: int, mat: torch.Tensor) -> None:
     """mat[C, C] (int64) += bincount(C * a[k] + b[k]) with k = (a >= 0) & (a < C)  (util/utils.py:106-109)."""
     if not (a.is_cuda and b.is_cuda):
@@ -87,6 +99,9 @@ def hist_pairs(a: torch.Tensor, b: torch.Tensor, C: int, mat: torch.Tensor) -> N
     b = b.long().contiguous()
     if a.numel() != b.numel():
         raise ValueError("a and b must have the same number of elements")
+    if (not mat.is_cuda or mat.device != a.device or b.device != a.device or mat.dtype != torch.int64
+            or not mat.is_contiguous() or mat.numel() != int(C) * int(C)):
+        raise ValueError("mat must be a contiguous int64 [C, C] tensor on the device of a and b")
     with torch.cuda.device(a.device):
         rc = _lib.lib().sf_hist_pairs(_ptr(a), _LABEL_CODE[a.dtype], _ptr(b), a.numel(), int(C), _ptr(mat), _stream(a.device))
     _lib.check(rc, "sf_hist_pairs")
@@ -95,14 +110,31 @@ def hist_pairs(a: torch.Tensor, b: torch.Tensor, C: int, mat: torch.Tensor) -> N
 def accumulate_counts(counts, hist_f32=None, hist_i64=None, mat=None) -> None:
     """One launch for the per-call bookkeeping of Metrics / ConfusionMatrix: hist_f32 += counts (float32 += int64, the
     reference's expression), hist_i64 += counts, mat += counts, counts = 0."""
+    if not counts.is_cuda or counts.dtype != torch.int64 or not counts.is_contiguous():
+        raise ValueError("counts must be a contiguous int64 CUDA tensor")
+    for name, t, dt in (("hist_f32", hist_f32, torch.float32), ("hist_i64", hist_i64, torch.int64), ("mat", mat, torch.int64)):
+        _check_cells(name, t, dt, counts)
     with torch.cuda.device(counts.device):
         rc = _lib.lib().sf_accumulate_counts(_ptr(counts), _ptr(hist_f32), _ptr(hist_i64), _ptr(mat), counts.numel(),
                                              _stream(counts.device))
     _lib.check(rc, "sf_accumulate_counts")
 
 
+def _onepass_enabled() -> bool:
+    """SF_NO_ONEPASS=1 forces the forward / finalize / backward kernel route (A/B measurement, tests)."""
+    return os.environ.get("SF_NO_ONEPASS", "0") != "1"
+
+
 class _FusedCE(torch.autograd.Function):
-    """upsample + (OHEM) cross-entropy; forward = sf_ce_forward + sf_loss_finalize, backward = sf_ce_backward."""
+    """upsample + (OHEM) cross-entropy.
+
+    Training (a gradient is wanted, shape covered by sf_onepass.cu): forward = sf_ce_onepass + sf_loss_finalize -- one walk
+    computes loss, confusion counts and the unscaled gradient -- and backward = sf_ce_onepass_backward (the global 1/K
+    scale, or the top-k re-walk when the device-side OHEM decision was branch 2).  Otherwise forward = sf_ce_forward +
+    sf_loss_finalize and backward = sf_ce_backward.  Second-order differentiation is not supported (once_differentiable):
+    the reference's `create_graph=is_second_order` path (engine.py:50-53, timm adahessian) raises here instead of silently
+    dropping the loss-curvature term.
+    """
 
     @staticmethod
     def forward(ctx, logits, labels, class_w, ignore, thresh, hist, focal=None):
@@ -117,14 +149,23 @@ class _FusedCE(torch.autograd.Function):
         ws_bytes = L.sf_workspace_bytes()
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         loss_px = torch.empty(n_px, dtype=torch.float32, device=dev) if keep_loss else None
-        lse_px = torch.empty(n_px, dtype=torch.float32, device=dev) if need_grad else None
         out = torch.empty((), dtype=torch.float32, device=dev)
+        lc, yc = _LOGIT_CODE[logits.dtype], _LABEL_CODE[labels.dtype]
+        onepass = (need_grad and focal is None and _onepass_enabled()
+                   and L.sf_ce_onepass_supported(lc, _ptr(logits), C, h, w, H, W) == 1)
+        lse_px = grad_acc = None
         with torch.cuda.device(dev):
             st = _stream(dev)
-            rc = L.sf_ce_forward(_ptr(logits), _LOGIT_CODE[logits.dtype], _ptr(labels), _LABEL_CODE[labels.dtype],
-                                 B, C, h, w, H, W, int(ignore), _ptr(class_w), float(thresh),
-                                 _ptr(loss_px), _ptr(lse_px), _ptr(hist), _ptr(ws), ws_bytes, st)
-            _lib.check(rc, "sf_ce_forward")
+            if onepass:
+                grad_acc = torch.empty((B, C, h, w), dtype=torch.float32, device=dev)
+                rc = L.sf_ce_onepass(_ptr(logits), lc, _ptr(labels), yc, B, C, h, w, H, W, int(ignore), _ptr(class_w),
+                                     float(thresh), _ptr(loss_px), _ptr(hist), _ptr(grad_acc), _ptr(ws), ws_bytes, st)
+                _lib.check(rc, "sf_ce_onepass")
+            else:
+                lse_px = torch.empty(n_px, dtype=torch.float32, device=dev) if need_grad else None
+                rc = L.sf_ce_forward(_ptr(logits), lc, _ptr(labels), yc, B, C, h, w, H, W, int(ignore), _ptr(class_w),
+                                     float(thresh), _ptr(loss_px), _ptr(lse_px), _ptr(hist), _ptr(ws), ws_bytes, st)
+                _lib.check(rc, "sf_ce_forward")
             if focal is None:
                 rc = L.sf_loss_finalize(_ptr(loss_px), n_px, float(thresh), _ptr(ws), ws_bytes, _ptr(out), st)
                 _lib.check(rc, "sf_loss_finalize")
@@ -135,23 +176,31 @@ class _FusedCE(torch.autograd.Function):
                 _lib.check(rc, "sf_focal_finalize")
         ctx.ignore = int(ignore)
         ctx.ws = ws                      # plain attribute: the workspace is an opaque device scratch
-        ctx.save_for_backward(logits, labels, class_w, loss_px, lse_px)
+        ctx.onepass = onepass
+        ctx.save_for_backward(logits, labels, class_w, loss_px, grad_acc if onepass else lse_px)
         return out
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_out):
-        logits, labels, class_w, loss_px, lse_px = ctx.saved_tensors
+        logits, labels, class_w, loss_px, aux = ctx.saved_tensors
         L = _lib.lib()
         B, C, h, w = logits.shape
         _, H, W = labels.shape
         dev = logits.device
         g = grad_out.detach().to(device=dev, dtype=torch.float32).contiguous()
         grad = torch.empty_like(logits)
+        lc, yc = _LOGIT_CODE[logits.dtype], _LABEL_CODE[labels.dtype]
         with torch.cuda.device(dev):
-            rc = L.sf_ce_backward(_ptr(logits), _LOGIT_CODE[logits.dtype], _ptr(labels), _LABEL_CODE[labels.dtype],
-                                  B, C, h, w, H, W, ctx.ignore, _ptr(class_w), _ptr(loss_px), _ptr(lse_px),
-                                  _ptr(g), _ptr(ctx.ws), _ptr(grad), _stream(dev))
-        _lib.check(rc, "sf_ce_backward")
+            if ctx.onepass:
+                rc = L.sf_ce_onepass_backward(_ptr(logits), lc, _ptr(labels), yc, B, C, h, w, H, W, ctx.ignore,
+                                              _ptr(class_w), _ptr(loss_px), _ptr(aux), _ptr(g), _ptr(ctx.ws), _ptr(grad),
+                                              _stream(dev))
+                _lib.check(rc, "sf_ce_onepass_backward")
+            else:
+                rc = L.sf_ce_backward(_ptr(logits), lc, _ptr(labels), yc, B, C, h, w, H, W, ctx.ignore, _ptr(class_w),
+                                      _ptr(loss_px), _ptr(aux), _ptr(g), _ptr(ctx.ws), _ptr(grad), _stream(dev))
+                _lib.check(rc, "sf_ce_backward")
         return grad, None, None, None, None, None, None
 
 
@@ -166,8 +215,9 @@ def fused_cross_entropy(logits, labels, weight=None, ignore_index=255, ohem_thre
     thresh = -1.0 if ohem_thresh is None else float(ohem_thresh)
     if ohem_thresh is not None and not (thresh >= 0.0 and math.isfinite(thresh)):
         raise ValueError("ohem_thresh must be a finite non-negative loss value")
-    if hist is not None and (hist.dtype != torch.int64 or hist.numel() != C * C or not hist.is_contiguous()):
-        raise ValueError("hist must be a contiguous int64 [C, C] tensor")
+    if hist is not None and (hist.dtype != torch.int64 or hist.numel() != C * C or not hist.is_contiguous()
+                             or hist.device != logits.device):
+        raise ValueError("hist must be a contiguous int64 [C, C] tensor on the logits' device")
     return _FusedCE.apply(logits, labels, cw, int(ignore_index), thresh, hist, None)
 
 
@@ -221,6 +271,7 @@ class _FusedCriterion(torch.autograd.Function):
         return out
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_out):
         logits, labels, lse_px, coef = ctx.saved_tensors
         L = _lib.lib()

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     L = _lib.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.sf_version() == 101
+    assert L.sf_version() == 200
     assert L.sf_dice_workspace_bytes(8, 19) >= 64 + 8 * 19 * 32 and L.sf_dice_workspace_bytes(0, 19) == 0
     assert L.sf_workspace_bytes() > 64
     assert L.sf_strerror(0) == b"ok" and b"argument" in L.sf_strerror(-1)
