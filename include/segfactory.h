@@ -146,7 +146,7 @@ int sf_ce_onepass(const void* logits, int ldtype, const void* labels, int ydtype
  *   branch 0 / 1 (CE, OHEM threshold): grad_logits = grad_acc * grad_out / denom (one streaming kernel);
  *   branch 2 (OHEM top-k fallback, util/losses.py:58-59): the speculative sums are void -- a second walk keeps the pixels
  *   with loss_px > k-th value (ties share, see sf_loss_state) and writes grad_logits directly.
- * Both kernels are always launched; each exits at once when the device-side branch is not its own.
+ * One launch either way: the CTAs read the device-side branch and either scale their slice or re-walk their tile.
  */
 int sf_ce_onepass_backward(const void* logits, int ldtype, const void* labels, int ydtype,
                            int B, int C, int h, int w, int H, int W, int ignore,

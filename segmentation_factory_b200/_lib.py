@@ -10,7 +10,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsegfactory.so")
+LIB_PATH = os.environ.get("SEGFACTORY_LIB") or os.path.join(_HERE, "libsegfactory.so")   # override: experiment builds
 
 SF_F32, SF_BF16, SF_F16 = 0, 1, 2
 SF_I64, SF_U8 = 0, 1

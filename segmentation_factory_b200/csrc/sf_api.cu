@@ -176,15 +176,17 @@ int sf_ce_onepass_backward(const void* logits, int ldtype, const void* labels, i
     if (!workspace || !grad_acc || !grad_logits) return SF_ERR_ARG;
     int rc = onepass_check(logits, ldtype, labels, ydtype, B, C, h, w, H, W);
     if (rc != SF_OK) return rc;
-    if (loss_px) {                                                   // plain CE keeps no loss vector and has no top-k branch
+    if (loss_px) {
+        // OHEM: one launch whose CTAs either scale their slice of grad_acc (branch 1) or re-walk their tile (branch 2)
         sf::OnepassArgs a{};
         a.logits = logits; a.ldtype = ldtype; a.labels = labels; a.ydtype = ydtype;
         a.B = B; a.C = C; a.h = h; a.w = w; a.H = H; a.W = W; a.ignore = ignore;
         a.class_w = class_w; a.thresh = 0.f; a.loss_px = const_cast<float*>(loss_px); a.grad_out = grad_out;
-        a.grad_logits = grad_logits; a.ws = const_cast<void*>(workspace); a.stream = stream; a.mode = 1; a.only_branch2 = 1;
-        rc = sf::launch_onepass(a);
-        if (rc != SF_OK) return rc;
+        a.grad_acc = const_cast<float*>(grad_acc); a.grad_logits = grad_logits; a.ws = const_cast<void*>(workspace);
+        a.stream = stream; a.mode = 1; a.only_branch2 = 1;
+        return sf::launch_onepass(a);
     }
+    // plain CE keeps no loss vector and has no top-k branch: the scale alone
     return sf::launch_onepass_scale(grad_acc, grad_logits, ldtype, (long long)B * C * h * w, grad_out, workspace, stream);
 }
 

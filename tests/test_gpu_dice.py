@@ -159,7 +159,8 @@ def test_dice_full_size_cityscapes_properties(sf):
     x2 = low.cuda().requires_grad_(True)
     l2 = sf.criterion(x2, lab.cuda(), None, num_classes=C, dice=False, ignore_index=255)
     l3 = sf.CrossEntropy(255)(low.cuda(), lab.cuda())
-    assert l2.item() == l3.item() and abs((total - dice) - l3.item()) <= 1e-5 * abs(l3.item())
+    # l2 wants a gradient (one-pass walk), l3 does not (forward kernel): same per-pixel terms, different summation order
+    assert abs(l2.item() - l3.item()) <= 2e-6 * abs(l3.item()) and abs((total - dice) - l3.item()) <= 1e-5 * abs(l3.item())
 
 
 def test_fused_ce_dice_forward_matches_two_launch_route(sf, oracle):
