@@ -314,7 +314,7 @@ def main():
     dev_sets = [(lo.to(dev), la.to(dev)) for lo, la in host_sets]
     ws = torch.zeros(ws_bytes, dtype=torch.uint8, device=dev)
     loss_px = torch.empty(n_px, dtype=torch.float32, device=dev)
-    lse_px = torch.empty(n_px, dtype=torch.float32, device=dev) if args.route == "split" else None
+    lse_px = torch.empty(n_px, dtype=torch.float32, device=dev)      # split route only
     grad_acc = torch.empty((B, C, LH, LW), dtype=torch.float32, device=dev)
     grad = torch.empty((B, C, LH, LW), dtype=torch.float32, device=dev)
     out = torch.empty((), dtype=torch.float32, device=dev)
@@ -322,7 +322,7 @@ def main():
     onepass = args.route == "onepass" and L.sf_ce_onepass_supported(0, dev_sets[0][0].data_ptr(), C, LH, LW, H, W) == 1
     geo = (B, C, LH, LW, H, W, 255)
 
-    def launch_step(sets, i, evs=None, reduce_every_step=False):
+    def launch_step(sets, i, evs=None, reduce_every_step=False, onepass=onepass):
         lo, la = sets[i % len(sets)]
         if evs:
             evs[0].record(stream)
@@ -353,14 +353,14 @@ def main():
         if work is not None:
             work.wait()                                          # stream-level wait, no host sync
 
-    def timed(sets, steps, reduce_every_step=False, sample_clocks=False):
+    def timed(sets, steps, reduce_every_step=False, sample_clocks=False, onepass=onepass):
         evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sampler = ClockSampler(torch, local) if (sample_clocks and rank == 0) else None
         barrier()
         e0.record(stream)
         for i in range(steps):
-            launch_step(sets, i, evs[i], reduce_every_step)
+            launch_step(sets, i, evs[i], reduce_every_step, onepass)
         if world > 1 and not reduce_every_step:
             # the path's one exchange (engine.py:100-101: once per evaluation, not per batch): the int64 matrix and
             # counters, one SUM over NVLink after the last step
@@ -557,7 +557,15 @@ def extra_legs(torch, sf, L, dev, args, launch_step, timed, peak, thr):
     ms, kern, _ = timed(sets, 10)
     out["cfg2_" + other] = {"ms": ms, "px_per_s": n_px2 / (ms * 1e-3), "kernel_ms": kern,
                            "frac": step_bpp * n_px2 / (ms * 1e-3) / 1e9 / peak,
-                           "note": "late = top-k branch: the one-pass walk's speculative sums are void, the backward re-walks"}
+                           "note": "late = top-k branch.  One-pass route: the walk's speculative sums are void, the backward re-walks "
+                                   "(what a FIRST late step costs; the Python API then learns the branch and switches route)"}
+    for i in range(3):
+        launch_step(sets, i, onepass=False)
+    ms, kern, _ = timed(sets, 10, onepass=False)
+    out["cfg2_" + other + "_split_route"] = {"ms": ms, "px_per_s": n_px2 / (ms * 1e-3), "kernel_ms": kern,
+                                            "frac": step_bpp * n_px2 / (ms * 1e-3) / 1e9 / peak,
+                                            "note": "sf_ce_forward + sf_loss_finalize + sf_ce_backward: the route the Python API takes once "
+                                                    "its branch hint says top-k"}
     del sets
 
     # configs[2] ADE20K plain CE fp32 C=150 B=16 and configs[3] COCO-Stuff bf16 C=171 B=16, fwd+bwd+matrix

@@ -107,7 +107,7 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return y;
 }
 
-// out[i] = acc[i] * s over a grid-strided slice (this CTA's share); four 128-bit loads in flight per thread
+// out[i] = acc[i] * s over a grid-strided slice (this CTA's share); eight 128-bit loads in flight per thread
 template <typename LT>
 __device__ __forceinline__ void scale_slice(const float* __restrict__ acc, LT* __restrict__ out, long long n, float s,
                                             long long first, long long stride) {
@@ -123,12 +123,12 @@ __device__ __forceinline__ void scale_slice(const float* __restrict__ acc, LT* _
         }
     };
     long long i = first;
-    for (; i + 3 * stride < n4; i += 4 * stride) {
-        float4 v[4];
+    for (; i + 7 * stride < n4; i += 8 * stride) {
+        float4 v[8];
         #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = __ldcs(a4 + i + u * stride);
+        for (int u = 0; u < 8; ++u) v[u] = __ldcs(a4 + i + u * stride);
         #pragma unroll
-        for (int u = 0; u < 4; ++u) put(i + u * stride, v[u]);
+        for (int u = 0; u < 8; ++u) put(i + u * stride, v[u]);
     }
     for (; i < n4; i += stride) put(i, __ldcs(a4 + i));
     for (long long j = 4 * n4 + first; j < n; j += stride) Logit<LT>::st(out + j, acc[j] * s);
@@ -227,14 +227,17 @@ onepass_kernel(const __grid_constant__ CUtensorMap tmap, const OpParams p) {
     const char* labp = lab_base + ((size_t)(colok ? X : 0) << lab_shift);          // label of the next row to fetch
     const size_t lab_stride = (size_t)p.W << lab_shift;
     float* lossp = loss_base + (colok ? X : 0);                     // FUSED: row being consumed (store); BWD: next row to fetch
-    int rows_left = colok ? Yb - Ya : 0;                            // rows still to fetch; the row being consumed is one behind
+    int rows_left = Yb - Ya;                                        // rows still to fetch; the row being consumed is one behind
+    // No guard around the loads (a guard is one more branch per row): the pointers stop at the tile's last row, which is
+    // then simply read again, and idle columns (outside the image) read column 0 and are masked by `colok`.
     auto fetch = [&]() {
-        if (rows_left > 0) {
-            nlo = p.label_u8 ? (int)__ldg(reinterpret_cast<const unsigned char*>(labp)) : __ldg(reinterpret_cast<const int*>(labp));
-            if (bwd_has_loss) nloss = __ldg(lossp);
+        nlo = p.label_u8 ? (int)__ldg(reinterpret_cast<const unsigned char*>(labp)) : __ldg(reinterpret_cast<const int*>(labp));
+        if (bwd_has_loss) nloss = __ldg(lossp);
+        --rows_left;
+        if (rows_left > 0) {                                         // CTA-uniform
+            labp += lab_stride;
+            if (!FUSED) lossp += p.W;
         }
-        labp += lab_stride; --rows_left;
-        if (!FUSED) lossp += p.W;
     };
     fetch();
     const int ign = p.ignore;
@@ -326,7 +329,7 @@ onepass_kernel(const __grid_constant__ CUtensorMap tmap, const OpParams p) {
         for (int r = TP::count(u, p.h); r > 0; --r, lh1 += lh1_step) {
             const int lo = nlo; const float loss_in = nloss;
             fetch();
-            const bool valid = (unsigned)lo < (unsigned)C && lo != ign;     // idle columns keep lo = -1
+            const bool valid = colok && (unsigned)lo < (unsigned)C && lo != ign;
             float l = 0.f;
             if (__any_sync(FULL, valid)) {
                 if (valid && lo != cur_y) {

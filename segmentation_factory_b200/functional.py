@@ -125,6 +125,38 @@ def _onepass_enabled() -> bool:
     return os.environ.get("SF_NO_ONEPASS", "0") != "1"
 
 
+class _BranchHint:
+    """Last OHEM decision seen on a device (sf_loss_state.branch), learnt WITHOUT a host sync: every backward enqueues a
+    4-byte copy of the state into pinned memory behind an event; the next forward uses the value only if that event has
+    already completed.  The one-pass walk speculates on the threshold branch (util/losses.py:56); when training has
+    settled on the top-k branch (:58-59) its gradient sums would be thrown away every step, so those steps take the
+    forward / finalize / backward kernels instead.  A stale or missing hint only costs time, never correctness: both
+    routes handle both branches."""
+    _by_device = {}
+
+    def __init__(self, dev):
+        self.host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.event = None
+
+    @classmethod
+    def last_branch(cls, dev):
+        h = cls._by_device.get(dev)
+        if h is None or h.event is None or torch.cuda.is_current_stream_capturing() or not h.event.query():
+            return None
+        return int(h.host[0])
+
+    @classmethod
+    def record(cls, dev, ws):
+        if torch.cuda.is_current_stream_capturing():
+            return
+        h = cls._by_device.get(dev)
+        if h is None:
+            h = cls._by_device[dev] = cls(dev)
+        h.host.copy_(ws[16:20].view(torch.int32), non_blocking=True)     # sf_loss_state.branch
+        h.event = torch.cuda.Event()
+        h.event.record(torch.cuda.current_stream(dev))
+
+
 class _FusedCE(torch.autograd.Function):
     """upsample + (OHEM) cross-entropy.
 
@@ -152,6 +184,7 @@ class _FusedCE(torch.autograd.Function):
         out = torch.empty((), dtype=torch.float32, device=dev)
         lc, yc = _LOGIT_CODE[logits.dtype], _LABEL_CODE[labels.dtype]
         onepass = (need_grad and focal is None and _onepass_enabled()
+                   and not (ohem and _BranchHint.last_branch(dev) == 2)
                    and L.sf_ce_onepass_supported(lc, _ptr(logits), C, h, w, H, W) == 1)
         lse_px = grad_acc = None
         with torch.cuda.device(dev):
@@ -177,6 +210,7 @@ class _FusedCE(torch.autograd.Function):
         ctx.ignore = int(ignore)
         ctx.ws = ws                      # plain attribute: the workspace is an opaque device scratch
         ctx.onepass = onepass
+        ctx.ohem = ohem
         ctx.save_for_backward(logits, labels, class_w, loss_px, grad_acc if onepass else lse_px)
         return out
 
@@ -201,6 +235,8 @@ class _FusedCE(torch.autograd.Function):
                 rc = L.sf_ce_backward(_ptr(logits), lc, _ptr(labels), yc, B, C, h, w, H, W, ctx.ignore, _ptr(class_w),
                                       _ptr(loss_px), _ptr(aux), _ptr(g), _ptr(ctx.ws), _ptr(grad), _stream(dev))
                 _lib.check(rc, "sf_ce_backward")
+            if loss_px is not None and ctx.ohem:
+                _BranchHint.record(dev, ctx.ws)
         return grad, None, None, None, None, None, None
 
 

@@ -207,3 +207,26 @@ def test_onepass_full_size_cityscapes_late_branch(sf):
     # handful of such pixels out of 8.4 M; everything else must agree to 1e-5.
     bad = ((x.grad - rg).abs() > 1e-5 * rg.abs().max()).sum().item()
     assert bad <= 4 * 4 * C, bad
+
+
+def test_branch_hint_switches_route_without_changing_results(sf, monkeypatch):
+    """After a step that ended on the top-k branch the next forward takes the forward / finalize / backward kernels (the
+    hint is read without a host sync, so synchronise first to make it visible); values equal the forced split route bit for bit."""
+    from segmentation_factory_b200 import functional as fn
+    low, lab = _synth(12, 2, 19, 64, 128, 256, 512, "late", blk=16)
+    monkeypatch.setenv("SF_NO_ONEPASS", "1")
+    l_ref, g_ref, _ = _run(sf, low, lab, None, THR, want_hist=False)
+    monkeypatch.setenv("SF_NO_ONEPASS", "0")
+    fn._BranchHint._by_device.clear()
+    l1, g1, _ = _run(sf, low, lab, None, THR, want_hist=False)                  # speculates, re-walks
+    torch.cuda.synchronize()
+    assert fn._BranchHint.last_branch(torch.device("cuda", torch.cuda.current_device())) == 2
+    l2, g2, _ = _run(sf, low, lab, None, THR, want_hist=False)                  # hinted: split route
+    assert l2.item() == l_ref.item() and torch.equal(g2, g_ref)
+    assert abs(l1.item() - l_ref.item()) <= 2e-6 * abs(l_ref.item())
+    assert (g1 - g_ref).abs().max().item() <= 1e-5 * g_ref.abs().max().item()
+    early, lab2 = _synth(11, 2, 19, 64, 128, 256, 512, "early", blk=16)
+    _run(sf, early, lab2, None, THR, want_hist=False)                          # threshold branch again -> hint resets
+    torch.cuda.synchronize()
+    assert fn._BranchHint.last_branch(torch.device("cuda", torch.cuda.current_device())) == 1
+    fn._BranchHint._by_device.clear()
