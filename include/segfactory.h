@@ -131,7 +131,7 @@ int sf_ce_backward(const void* logits, int ldtype, const void* labels, int ydtyp
  *   loss_px   [B*H*W] fp32, required when ohem_thresh >= 0 (the top-k fallback selects from it), else nullable
  *   hist      [C*C] accumulated, nullable
  *   grad_acc  [B*C*h*w] fp32 scratch: unscaled gradient sums, overwritten
- * Returns SF_ERR_UNSUPPORTED for shapes outside the one-pass kernels (H == S*h, W == S*w, S in {4, 8}, C in {19, 21},
+ * Returns SF_ERR_UNSUPPORTED for shapes outside the one-pass kernels (H == S*h, W == S*w, S in {4, 8}, C in {2, 9, 19, 21},
  * 16-byte aligned rows); sf_ce_onepass_supported() tells beforehand.  Nothing is launched in that case.
  */
 int sf_ce_onepass_supported(int ldtype, const void* logits, int C, int h, int w, int H, int W);

@@ -10,10 +10,10 @@ backed by hand-written sm_100a kernels in libsegfactory.so (C ABI: include/segfa
 """
 from .labels import LabelLUT
 from .losses import CrossEntropy, FocalLoss, OhemCrossEntropy, get_loss
-from .metrics import ConfusionMatrix, Metrics, fused_eval_update
+from .metrics import ConfusionMatrix, Metrics, fused_eval_update, reduce_from_all_processes
 from .engine import criterion
 from .functional import eval_hist, fused_criterion, fused_cross_entropy, fused_focal_loss, hist_pairs
 
 __all__ = ["CrossEntropy", "OhemCrossEntropy", "FocalLoss", "fused_focal_loss", "get_loss", "Metrics", "ConfusionMatrix",
-           "fused_eval_update", "fused_cross_entropy", "fused_criterion", "criterion", "eval_hist", "hist_pairs", "LabelLUT"]
-__version__ = "0.1.0"
+           "fused_eval_update", "reduce_from_all_processes", "fused_cross_entropy", "fused_criterion", "criterion", "eval_hist", "hist_pairs", "LabelLUT"]
+__version__ = "0.2.0"

@@ -21,7 +21,7 @@ bool onepass_supported(int ldtype, const void* logits, int C, int h, int w, int 
     if (env_no_tma() || env_no_fast() || h <= 0 || w <= 0 || H % h || W % w) return false;
     const int s = H / h;
     if (s != W / w || (s != 4 && s != 8)) return false;
-    if (C != 19 && C != 21) return false;
+    if (C != 19 && C != 21 && C != 9 && C != 2) return false;        // train_gpu.py:48-49 class counts that fit the registers
     const int esz = ldtype == SF_F32 ? 4 : 2;
     if (((size_t)w * esz) % 16 || ((uintptr_t)logits % 16)) return false;
     const int xal = 16 / esz;

@@ -434,7 +434,9 @@ onepass_kernel(const __grid_constant__ CUtensorMap tmap, const OpParams p) {
                             hrun_key = key;
                         }
                     }
-                    if (__any_sync(FULL, work)) {
+                    // FUSED: no second vote -- on the threshold branch nearly every valid pixel is kept (steps that settle on
+                    // the top-k branch are routed to the forward / backward kernels by the caller's branch hint)
+                    if (FUSED || __any_sync(FULL, work)) {
                         const float cf = work ? coef * rcp_approx(ssum) : 0.f;
                         const float v0 = cf * lh0, v1 = cf * lh1;
                         const float2 v0_2 = splat(v0), v1_2 = splat(v1);
@@ -547,7 +549,10 @@ inline int op_launch(const OnepassArgs& a) {
     CUtensorMap tmap{};
     const int rc = make_logits_tmap(&tmap, a.logits, a.ldtype, a.B * a.C, a.h, a.w, C, G::BH, G::BW);
     if (rc != 0) return rc;
-    const size_t smem = G::smem(HIST);
+    size_t smem = G::smem(HIST);
+#ifdef SF_OP_EXPERIMENT
+    if (const char* pad = std::getenv("SF_DEBUG_SMEM_PAD_KB")) smem += (size_t)atoi(pad) * 1024;   // occupancy sensitivity knob
+#endif
     auto k = onepass_kernel<LT, C, S, TH, MINB, UNR, MODE, OHEM, HIST>;
     static bool attr_set_dev[64] = {};                               // per instantiation and device; idempotent, so a race is harmless
     int dev = 0; cudaGetDevice(&dev);
@@ -613,6 +618,8 @@ inline int op_classes(const OnepassArgs& a, int s) {
         case 19: return op_scale<LT, 19>(a, s);
 #ifndef SF_OP_EXPERIMENT
         case 21: return op_scale<LT, 21>(a, s);
+        case 9: return op_scale<LT, 9>(a, s);                       // Synapse (train_gpu.py:48-49)
+        case 2: return op_scale<LT, 2>(a, s);                       // Kvasir (binary)
 #endif
         default: return SF_ERR_UNSUPPORTED;
     }

@@ -131,7 +131,8 @@ class _BranchHint:
     already completed.  The one-pass walk speculates on the threshold branch (util/losses.py:56); when training has
     settled on the top-k branch (:58-59) its gradient sums would be thrown away every step, so those steps take the
     forward / finalize / backward kernels instead.  A stale or missing hint only costs time, never correctness: both
-    routes handle both branches."""
+    routes handle both branches (their results agree to float rounding, not bit for bit: SF_NO_BRANCH_HINT=1 pins the route
+    when bitwise run-to-run reproducibility across a branch change matters)."""
     _by_device = {}
 
     def __init__(self, dev):
@@ -140,6 +141,8 @@ class _BranchHint:
 
     @classmethod
     def last_branch(cls, dev):
+        if os.environ.get("SF_NO_BRANCH_HINT", "0") == "1":          # fixed route: bitwise-identical steps regardless of history
+            return None
         h = cls._by_device.get(dev)
         if h is None or h.event is None or torch.cuda.is_current_stream_capturing() or not h.event.query():
             return None

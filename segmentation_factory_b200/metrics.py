@@ -143,9 +143,32 @@ class ConfusionMatrix(object):
                 iu.mean().item() * 100)
 
 
+def reduce_from_all_processes(metric: Metrics, confmat: ConfusionMatrix) -> None:
+    """engine.py:100-101 (confmat.reduce_from_all_processes(); metric.reduce_from_all_processes()) as ONE collective:
+    both int64 matrices travel in a single packed all_reduce(SUM) -- the message is a few KB, so the cost is latency and
+    two collectives cost twice that.  Integer SUM is order-independent, so every rank ends with identical matrices."""
+    if not dist.is_available() or not dist.is_initialized():
+        return
+    confmat._ensure(metric.hist_i64.device)
+    n = metric.hist_i64.numel()
+    packed = torch.cat([metric.hist_i64.reshape(-1), confmat.mat.reshape(-1).to(metric.hist_i64.device)])
+    dist.all_reduce(packed)
+    metric.hist_i64.copy_(packed[:n].view_as(metric.hist_i64))
+    metric.hist = metric.hist_i64.to(torch.float32)
+    confmat.mat.copy_(packed[n:].view_as(confmat.mat))
+
+
 def fused_eval_update(logits: Tensor, labels: Tensor, metric: Metrics, confmat: ConfusionMatrix, size=None) -> None:
     """One kernel launch feeding both accumulators of engine.evaluate (engine.py:90-91): the reference takes
-    two argmax passes over materialised full-resolution logits and builds two histograms."""
+    two argmax passes over materialised full-resolution logits and builds two histograms.
+
+    The two reference accumulators mask differently: Metrics drops `ignore_label`, ConfusionMatrix keeps every label in
+    [0, C).  They agree exactly when the ignore label lies outside [0, C) (255 everywhere in the reference); an in-range
+    ignore label would silently drop that row from the confusion matrix, so it is refused here -- use
+    confmat.update(a, b) + metric.update(...) for that case."""
+    if 0 <= int(metric.ignore_label) < int(confmat.num_classes):
+        raise ValueError(f"fused_eval_update needs an ignore label outside [0, {confmat.num_classes}); "
+                         f"got {metric.ignore_label}: update the two accumulators separately")
     counts = metric._scratch(logits.device)
     eval_hist(logits, labels, metric.ignore_label, counts, size)
     confmat._ensure(logits.device)

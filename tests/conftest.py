@@ -60,3 +60,15 @@ def oracle():
     from oracle import oracle as orc
     orc.build()
     return orc
+
+
+@pytest.fixture(autouse=True)
+def _fresh_branch_hint():
+    """The OHEM branch hint (functional._BranchHint) is process-wide state: without this a test's route would depend on
+    which test ran before it."""
+    try:
+        from segmentation_factory_b200 import functional as fn
+        fn._BranchHint._by_device.clear()
+    except Exception:
+        pass
+    yield

@@ -65,13 +65,13 @@ def digest(a: np.ndarray) -> str:
 
 
 def run_case(name, seed, B, C, hw, HW, kind, dtype=torch.float32, ldt=torch.int64, loss="ohem",
-             weighted=False, store_up=False, all_ignored=False, flip_p=0.03):
+             weighted=False, store_up=False, all_ignored=False, flip_p=0.03, low_override=None):
     g = torch.Generator().manual_seed(seed)
     (h, w), (H, W) = hw, HW
     labels = make_labels(g, B, C, H, W, dtype=ldt)
     if all_ignored:
         labels.fill_(255)
-    low = make_logits(g, kind, B, C, h, w, labels, flip_p).to(dtype)
+    low = make_logits(g, kind, B, C, h, w, labels, flip_p).to(dtype) if low_override is None else low_override
     cw = torch.rand(C, generator=torch.Generator().manual_seed(7)) + 0.5 if weighted else None
 
     lowg = low.clone().requires_grad_(True)

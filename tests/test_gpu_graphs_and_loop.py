@@ -21,7 +21,9 @@ def sf():
     return m
 
 
-def test_cuda_graph_capture_and_replay(sf):
+def test_cuda_graph_capture_and_replay(sf, monkeypatch):
+    # eager steps would switch kernels after a top-k step (branch hint); a captured graph replays one fixed route
+    monkeypatch.setenv("SF_NO_BRANCH_HINT", "1")
     B, C = 2, 19
     sets = [_synth(300 + i, B, C, 64, 128, 256, 512, "early" if i % 2 == 0 else "late") for i in range(3)]
     x_static = sets[0][0].cuda().clone().requires_grad_(True)

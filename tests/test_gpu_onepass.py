@@ -43,6 +43,11 @@ ONEPASS_CASES = [
     ("c19_x8_ce", 17, 1, 19, 20, 36, 160, 288, "early", torch.float32, torch.int64, "ce", False),
     ("c19_x4_bf16_ce", 18, 3, 19, 10, 40, 40, 160, "early", torch.bfloat16, torch.int64, "ce", False),
     ("c19_x4_ragged_tiles", 19, 1, 19, 27, 92, 108, 368, "late", torch.float32, torch.int64, "ohem", False),
+    ("c2_x4_ce_weighted_u8", 31, 2, 2, 40, 64, 160, 256, "early", torch.float32, torch.uint8, "ce", True),
+    ("c2_x8_bf16_ohem", 32, 1, 2, 20, 48, 160, 384, "early", torch.bfloat16, torch.int64, "ohem", False),
+    ("c9_x4_late_ohem", 33, 2, 9, 36, 72, 144, 288, "late", torch.float32, torch.int64, "ohem", False),
+    ("c9_x8_fp16_ce", 34, 1, 9, 18, 40, 144, 320, "early", torch.float16, torch.int64, "ce", False),
+    ("c19_x4_tall_tiles", 35, 6, 19, 96, 160, 384, 640, "early", torch.float32, torch.int64, "ohem", False),
 ]
 
 
@@ -75,7 +80,7 @@ def test_onepass_vs_oracle_and_split_route(sf, oracle, case, monkeypatch):
     assert torch.equal(hist, hist_s)
     if lk == "ohem":
         ref_loss, ref_grad, info = oracle.ohem_loss_and_grad(lown, labn, 255, cwn, ldtype=od)
-        if name in ("c19_x4_late_ohem", "c19_x4_ragged_tiles"):
+        if name in ("c19_x4_late_ohem", "c19_x4_ragged_tiles", "c9_x4_late_ohem"):
             assert info["branch"] == 1, info                                   # oracle numbering: 1 = top-k fallback
     else:
         ref_loss, ref_grad = oracle.ce_loss_and_grad(lown, labn, 255, cwn, od)
