@@ -61,6 +61,7 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
     constexpr int NP = G::NP;
     constexpr bool CSTAT = MODE == FF_SOFTMAX_STATS;                // CE forward that also gathers the dice sums (criterion)
     constexpr bool NOHIST = MODE == FF_SOFTMAX_NOHIST;              // loss only (training without metrics): no argmax index
+    constexpr bool NEED_IDX = MODE == FF_ARGMAX || MODE == FF_SOFTMAX;   // the modes that can feed the confusion matrix
     constexpr bool SOFTMAX = MODE == FF_SOFTMAX || CSTAT || NOHIST;
     constexpr bool DSTAT = MODE == FF_DICE_STATS, DCOEF = MODE == FF_DICE_COEF, DICE = DSTAT || DCOEF;
     constexpr bool ACCP = DSTAT || CSTAT;                           // per-thread sum p_k accumulators + shared bins
@@ -249,11 +250,25 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
                 float m = G::ODD ? zl : z[NP - 1].y;
                 #pragma unroll
                 for (int q = 0; q < NP; ++q) m = fmaxf(m, fmaxf(z[q].x, z[q].y));
-                int idx = C - 1;
-                #pragma unroll
-                for (int q = NP - 1; q >= 0; --q) {
-                    idx = (z[q].y == m) ? 2 * q + 1 : idx;
-                    idx = (z[q].x == m) ? 2 * q : idx;
+                // First index attaining the maximum without a compare/select chain (2 ALU-pipe ops per channel, the pipe this
+                // kernel saturates): d_k = z_k - m is +0 exactly at the maximum and has its sign bit set elsewhere, so one funnel
+                // shift per channel collects the "below the maximum" bits and the index is the lowest clear bit.  +-0 maxima
+                // (-0 == +0 for torch) and NaN / Inf take the exact slow path below.
+                int idx = 0;
+                if (NEED_IDX) {
+                    const float2 nm = splat(-m);
+                    unsigned bits_lo = 0u, bits_hi = 0u;
+                    constexpr int CH = C / 2;
+                    if (G::ODD) bits_hi = __funnelshift_l(__float_as_uint(zl - m), bits_hi, 1);
+                    #pragma unroll
+                    for (int q = NP - 1; q >= 0; --q) {
+                        const float2 d = __fadd2_rn(z[q], nm);
+                        if (2 * q + 1 >= CH) bits_hi = __funnelshift_l(__float_as_uint(d.y), bits_hi, 1);
+                        else bits_lo = __funnelshift_l(__float_as_uint(d.y), bits_lo, 1);
+                        if (2 * q >= CH) bits_hi = __funnelshift_l(__float_as_uint(d.x), bits_hi, 1);
+                        else bits_lo = __funnelshift_l(__float_as_uint(d.x), bits_lo, 1);
+                    }
+                    idx = __ffs(~((bits_hi << CH) | bits_lo)) - 1;
                 }
                 float ssum = 1.f;
                 const float m2 = __fmul_rn(m, kLog2e);
@@ -275,8 +290,10 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
                         if (CSTAT) zl = exl;
                     }
                 }
-                const bool weird = SOFTMAX ? (ssum != ssum) : (nanflag != nanflag);
-                if (weird) {                                         // torch: NaN beats everything, first NaN wins
+                const bool weird = (SOFTMAX ? (ssum != ssum) : (nanflag != nanflag)) || m == 0.f;
+                if (weird && NEED_IDX) {                              // torch: NaN beats everything, first NaN wins; -0 == +0
+                    idx = -1;
+                    int first_eq = C - 1;
                     #pragma unroll 1
                     for (int k = C - 1; k >= 0; --k) {
                         const LT* qk = Sg + k * G::PLANE;
@@ -284,7 +301,9 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
                         const float t1 = lerp_pinned(Logit<LT>::ld(qk + o1 + cj0), lw0, Logit<LT>::ld(qk + o1 + cj1), lw1);
                         const float zk = Logit<LT>::rnd(lerp_pinned(t0, lh0, t1, lh1));
                         if (zk != zk) idx = k;
+                        if (zk == m) first_eq = k;
                     }
+                    if (idx < 0) idx = first_eq;
                 }
                 const int lab = (int)(labs & 0xffu);
                 const bool valid = lab != 255;
