@@ -231,6 +231,15 @@ int sf_hist_pairs(const void* a, int adtype, const long long* b, long long n, in
 int sf_accumulate_counts(unsigned long long* counts, float* hist_f32, long long* hist_i64, long long* mat,
                          int n, void* stream);
 
+/*
+ * engine.py:90-91 for one batch in ONE call: sf_eval_hist into `counts` (device scratch of C*C, zero on entry, zero again on
+ * return) followed by sf_accumulate_counts into the caller's accumulators.  Same kernels, one crossing of the language
+ * boundary: at validation batch size 1 the host side of two calls costs more than the 17 us of GPU work per image.
+ */
+int sf_eval_update(const void* logits, int ldtype, const void* labels, int ydtype,
+                   int B, int C, int h, int w, int H, int W, int ignore,
+                   unsigned long long* counts, float* hist_f32, long long* hist_i64, long long* mat, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,9 +8,12 @@
 namespace sf {
 
 int sm_count() {
+    static int cached[64] = {};                                      // per device; the attribute query is a driver round trip
     int dev = 0, n = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cached[dev & 63] > 0) return cached[dev & 63];
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+    cached[dev & 63] = n;
     return n;
 }
 
@@ -263,6 +266,13 @@ int sf_accumulate_counts(unsigned long long* counts, float* hist_f32, long long*
                          void* stream) {
     if (!counts || n <= 0) return SF_ERR_ARG;
     return sf::launch_accumulate_counts(counts, hist_f32, hist_i64, mat, n, stream);
+}
+
+int sf_eval_update(const void* logits, int ldtype, const void* labels, int ydtype, int B, int C, int h, int w, int H, int W,
+                   int ignore, unsigned long long* counts, float* hist_f32, long long* hist_i64, long long* mat, void* stream) {
+    const int rc = sf_eval_hist(logits, ldtype, labels, ydtype, B, C, h, w, H, W, ignore, counts, stream);
+    if (rc != SF_OK) return rc;
+    return sf::launch_accumulate_counts(counts, hist_f32, hist_i64, mat, C * C, stream);
 }
 
 int sf_hist_pairs(const void* a, int adtype, const long long* b, long long n, int C, unsigned long long* mat,

@@ -369,7 +369,8 @@ static int bf_launch_d(const BwdArgs& a) {
     size_t smem = (size_t)G::SRC_BYTES + (size_t)2 * C * kBfThreads * 4 + 16;
     if (const char* pad = std::getenv("SF_DEBUG_SMEM_PAD_KB")) smem += (size_t)atoi(pad) * 1024;   // experiment knob (occupancy sensitivity)
     auto k = bwd_fast_kernel<LT, C, S, CHUNK, DICE>;
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static SmemLimitOnce smem_once;                                  // per instantiation
+    cudaError_t e = set_smem_limit_once(k, smem, smem_once);
     if (e != cudaSuccess) return (int)e;
     k<<<(int)grid, kBfThreads, smem, reinterpret_cast<cudaStream_t>(a.stream)>>>(tmap, p);
     return (int)cudaGetLastError();

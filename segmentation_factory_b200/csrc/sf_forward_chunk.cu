@@ -462,11 +462,10 @@ static int fc_launch(const FwdArgs& a) {
     const int rc = make_logits_tmap(&tmap, a.logits, a.ldtype, a.B * a.C, a.h, a.w, kFcNCH, G::BH, G::BW);
     if (rc != 0) return rc;
     auto k = fwd_chunk_kernel<LT, S, MODE>;
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static SmemLimitOnce smem_once;                                  // per instantiation
+    cudaError_t e = set_smem_limit_once(k, smem, smem_once);
     if (e != cudaSuccess) return (int)e;
-    int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kFcThreads, smem);
-    if (per_sm < 1) per_sm = 1;
+    int per_sm = 1;                                                  // 512 threads x ~120 registers: one CTA per SM
     const int grid = (int)std::min<long long>(total, std::min(kMaxCtas, per_sm * sm_count()));
     k<<<grid, kFcThreads, smem, reinterpret_cast<cudaStream_t>(a.stream)>>>(tmap, p);
     return (int)cudaGetLastError();

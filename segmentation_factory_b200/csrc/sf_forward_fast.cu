@@ -526,7 +526,8 @@ static int ff_launch(const FwdArgs& a) {
         smem += (size_t)2 * a.B * (C + (C & 1)) * 4;
     }
     auto k = fwd_fast_kernel<LT, C, S, MODE>;
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static SmemLimitOnce smem_once;                                  // per instantiation
+    cudaError_t e = set_smem_limit_once(k, smem, smem_once);
     if (e != cudaSuccess) return (int)e;
     const char* gm = std::getenv("SF_DEBUG_CTAS_PER_SM");             // experiment knob (occupancy sensitivity)
     const int per_sm = gm ? std::max(1, atoi(gm)) : 2;

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda.h>
+#include <cuda_runtime.h>
 #include <stddef.h>
 
 #include <algorithm>
@@ -99,6 +100,20 @@ int launch_hist_pairs(const void* a, int adtype, const long long* b, long long n
 int make_logits_tmap(CUtensorMap* map, const void* logits, int ldtype, int planes, int h, int w,
                      int box_c, int box_h, int box_w);
 int sm_count();
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) costs ~1.5 us per call: do it once per kernel instantiation and device
+// (`slot` is a function-local static of the launcher; a larger limit set earlier also covers a smaller request).
+struct SmemLimitOnce { int bytes[64] = {}; };
+template <typename K>
+inline cudaError_t set_smem_limit_once(K kernel, size_t smem, SmemLimitOnce& slot) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& have = slot.bytes[dev & 63];
+    if (have >= (int)smem) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) have = (int)smem;
+    return e;
+}
 bool env_no_tma();
 bool env_no_fast();   // SF_NO_FAST=1: always take the generic kernels (A/B measurement, tests)
 

@@ -554,14 +554,9 @@ inline int op_launch(const OnepassArgs& a) {
     if (const char* pad = std::getenv("SF_DEBUG_SMEM_PAD_KB")) smem += (size_t)atoi(pad) * 1024;   // occupancy sensitivity knob
 #endif
     auto k = onepass_kernel<LT, C, S, TH, MINB, UNR, MODE, OHEM, HIST>;
-    static bool attr_set_dev[64] = {};                               // per instantiation and device; idempotent, so a race is harmless
-    int dev = 0; cudaGetDevice(&dev);
-    bool& attr_set = attr_set_dev[dev & 63];
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
+    static SmemLimitOnce smem_once;                                  // per instantiation
+    const cudaError_t ea = set_smem_limit_once(k, smem, smem_once);
+    if (ea != cudaSuccess) return (int)ea;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(a.stream);
     if (MODE == OP_FUSED) {
         Workspace* w = reinterpret_cast<Workspace*>(a.ws);

@@ -18,7 +18,31 @@ _LABEL_CODE = {torch.int64: _lib.SF_I64, torch.uint8: _lib.SF_U8}
 
 
 def _stream(device) -> int:
-    return torch.cuda.current_stream(device).cuda_stream
+    """Raw cudaStream_t of torch's current stream on `device` (torch.cuda.current_stream() builds a Stream object: 3.5 us)."""
+    idx = device.index
+    return torch._C._cuda_getCurrentRawStream(idx if idx is not None else torch.cuda.current_device())
+
+
+class _on_device:
+    """Make `device` current around a C-ABI call, skipping the guard (2 us) when it already is -- the per-call host cost
+    matters at validation batch size 1 (engine.py:83-91 runs one image per step)."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, device):
+        self.idx = device.index
+        self.prev = -1
+
+    def __enter__(self):
+        if self.idx is not None:
+            cur = torch.cuda.current_device()
+            if cur != self.idx:
+                self.prev = cur
+                torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *exc):
+        if self.prev >= 0:
+            torch.cuda.set_device(self.prev)
+        return False
 
 
 def _ptr(t):
@@ -71,7 +95,7 @@ def eval_hist(logits: torch.Tensor, labels: torch.Tensor, ignore: int, hist: tor
     if hist.dtype != torch.int64 or not hist.is_contiguous() or hist.numel() != C * C or hist.device != logits.device:
         raise ValueError("hist must be a contiguous int64 [C, C] tensor on the logits' device")
     _, H, W = labels.shape
-    with torch.cuda.device(logits.device):
+    with _on_device(logits.device):
         rc = _lib.lib().sf_eval_hist(_ptr(logits), _LOGIT_CODE[logits.dtype], _ptr(labels), _LABEL_CODE[labels.dtype],
                                      B, C, h, w, H, W, int(ignore), _ptr(hist), _stream(logits.device))
     _lib.check(rc, "sf_eval_hist")
@@ -85,6 +109,23 @@ def _check_cells(name, t, dtype, like) -> None:
     if not t.is_cuda or t.device != like.device or t.dtype != dtype or not t.is_contiguous() or t.numel() != like.numel():
         raise ValueError(f"{name} must be a contiguous {dtype} tensor with {like.numel()} cells on {like.device} "
                          f"(got {t.dtype}, {tuple(t.shape)}, {t.device})")
+
+
+def eval_update(logits, labels, ignore, counts, hist_f32=None, hist_i64=None, mat=None, size=None) -> None:
+    """eval_hist + accumulate_counts through ONE C-ABI call (sf_eval_update): `counts` is the zeroed int64 [C, C] scratch."""
+    logits = prep_logits(logits)
+    B, C, h, w = logits.shape
+    labels = prep_labels(labels, B, size if size is not None else (h, w))
+    if counts.dtype != torch.int64 or not counts.is_contiguous() or counts.numel() != C * C or counts.device != logits.device:
+        raise ValueError("counts must be a contiguous int64 [C, C] tensor on the logits' device")
+    for name, t, dt in (("hist_f32", hist_f32, torch.float32), ("hist_i64", hist_i64, torch.int64), ("mat", mat, torch.int64)):
+        _check_cells(name, t, dt, counts)
+    _, H, W = labels.shape
+    with _on_device(logits.device):
+        rc = _lib.lib().sf_eval_update(_ptr(logits), _LOGIT_CODE[logits.dtype], _ptr(labels), _LABEL_CODE[labels.dtype],
+                                       B, C, h, w, H, W, int(ignore), _ptr(counts), _ptr(hist_f32), _ptr(hist_i64), _ptr(mat),
+                                       _stream(logits.device))
+    _lib.check(rc, "sf_eval_update")
 
 
 def hist_pairs(a: torch.Tensor, b: torch.Tensor, C: int, mat: torch.Tensor) -> None:
@@ -102,7 +143,7 @@ def hist_pairs(a: torch.Tensor, b: torch.Tensor, C: int, mat: torch.Tensor) -> N
     if (not mat.is_cuda or mat.device != a.device or b.device != a.device or mat.dtype != torch.int64
             or not mat.is_contiguous() or mat.numel() != int(C) * int(C)):
         raise ValueError("mat must be a contiguous int64 [C, C] tensor on the device of a and b")
-    with torch.cuda.device(a.device):
+    with _on_device(a.device):
         rc = _lib.lib().sf_hist_pairs(_ptr(a), _LABEL_CODE[a.dtype], _ptr(b), a.numel(), int(C), _ptr(mat), _stream(a.device))
     _lib.check(rc, "sf_hist_pairs")
 
@@ -114,7 +155,7 @@ def accumulate_counts(counts, hist_f32=None, hist_i64=None, mat=None) -> None:
         raise ValueError("counts must be a contiguous int64 CUDA tensor")
     for name, t, dt in (("hist_f32", hist_f32, torch.float32), ("hist_i64", hist_i64, torch.int64), ("mat", mat, torch.int64)):
         _check_cells(name, t, dt, counts)
-    with torch.cuda.device(counts.device):
+    with _on_device(counts.device):
         rc = _lib.lib().sf_accumulate_counts(_ptr(counts), _ptr(hist_f32), _ptr(hist_i64), _ptr(mat), counts.numel(),
                                              _stream(counts.device))
     _lib.check(rc, "sf_accumulate_counts")
@@ -190,7 +231,7 @@ class _FusedCE(torch.autograd.Function):
                    and not (ohem and _BranchHint.last_branch(dev) == 2)
                    and L.sf_ce_onepass_supported(lc, _ptr(logits), C, h, w, H, W) == 1)
         lse_px = grad_acc = None
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             st = _stream(dev)
             if onepass:
                 grad_acc = torch.empty((B, C, h, w), dtype=torch.float32, device=dev)
@@ -228,7 +269,7 @@ class _FusedCE(torch.autograd.Function):
         g = grad_out.detach().to(device=dev, dtype=torch.float32).contiguous()
         grad = torch.empty_like(logits)
         lc, yc = _LOGIT_CODE[logits.dtype], _LABEL_CODE[labels.dtype]
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             if ctx.onepass:
                 rc = L.sf_ce_onepass_backward(_ptr(logits), lc, _ptr(labels), yc, B, C, h, w, H, W, ctx.ignore,
                                               _ptr(class_w), _ptr(loss_px), _ptr(aux), _ptr(g), _ptr(ctx.ws), _ptr(grad),
@@ -289,7 +330,7 @@ class _FusedCriterion(torch.autograd.Function):
         out = torch.empty((), dtype=torch.float32, device=dev)
         geo = (B, C, h, w, H, W, int(ignore))
         coef = None
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             st = _stream(dev)
             lc, yc = _LOGIT_CODE[logits.dtype], _LABEL_CODE[labels.dtype]
             rc = L.sf_ce_dice_forward(_ptr(logits), lc, _ptr(labels), yc, *geo, _ptr(class_w), _ptr(lse_px),
@@ -317,7 +358,7 @@ class _FusedCriterion(torch.autograd.Function):
         dev = logits.device
         g = grad_out.detach().to(device=dev, dtype=torch.float32).contiguous()
         grad = torch.empty_like(logits)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             rc = L.sf_dice_backward(_ptr(logits), _LOGIT_CODE[logits.dtype], _ptr(labels), _LABEL_CODE[labels.dtype],
                                     *ctx.geo, _ptr(lse_px), _ptr(coef[0]), _ptr(coef[1]), _ptr(ctx.dws), ctx.dws.numel(),
                                     _ptr(g), _ptr(grad), _stream(dev))

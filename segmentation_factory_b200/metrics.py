@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 from torch import Tensor
 
-from .functional import accumulate_counts, eval_hist, hist_pairs
+from .functional import accumulate_counts, eval_hist, eval_update, hist_pairs
 
 __all__ = ["Metrics", "ConfusionMatrix", "fused_eval_update"]
 
@@ -39,9 +39,7 @@ class Metrics:
     def update(self, pred: Tensor, target: Tensor, size=None) -> None:
         """pred: [B, C, h, w] logits at any resolution; target: [B, H, W] labels, or the flattened vector
         engine.py:91 passes (then H, W = `size`, defaulting to pred's own h, w)."""
-        counts = self._scratch(pred.device)
-        eval_hist(pred, target, self.ignore_label, counts, size)
-        accumulate_counts(counts, self.hist, self.hist_i64, None)
+        eval_update(pred, target, self.ignore_label, self._scratch(pred.device), self.hist, self.hist_i64, None, size)
 
     def update_pq(self, gt_masks, pred_masks, iou_threshold=0.5):
         """util/metrics.py:50-91 (instance-mask matching for panoptic quality).  Nothing in the reference calls it and it is not
@@ -169,7 +167,6 @@ def fused_eval_update(logits: Tensor, labels: Tensor, metric: Metrics, confmat: 
     if 0 <= int(metric.ignore_label) < int(confmat.num_classes):
         raise ValueError(f"fused_eval_update needs an ignore label outside [0, {confmat.num_classes}); "
                          f"got {metric.ignore_label}: update the two accumulators separately")
-    counts = metric._scratch(logits.device)
-    eval_hist(logits, labels, metric.ignore_label, counts, size)
     confmat._ensure(logits.device)
-    accumulate_counts(counts, metric.hist, metric.hist_i64, confmat.mat)     # 2 launches per batch in total
+    eval_update(logits, labels, metric.ignore_label, metric._scratch(logits.device), metric.hist, metric.hist_i64, confmat.mat,
+                size)                                                       # one C-ABI call, 2 launches per batch
