@@ -240,6 +240,20 @@ int sf_eval_update(const void* logits, int ldtype, const void* labels, int ydtyp
                    int B, int C, int h, int w, int H, int W, int ignore,
                    unsigned long long* counts, float* hist_f32, long long* hist_i64, long long* mat, void* stream);
 
+/*
+ * The decode head's 1x1 classifier, the producer of the low-resolution logits: replaces
+ * nn.Conv2d(embed_dim, num_classes, 1) -- SegFormerHead.linear_pred (models/heads/segformer.py:39,57), UPerHead.conv_seg
+ * (models/heads/upernet.py:32,50), FPNHead.conv_seg (models/heads/fpn.py:23,37) -- forward only:
+ *     logits[b][c][i][j] = bias[c] + sum_k weight[c][k] * x[b][k][i][j]
+ * x [B,K,h,w] and weight [C,K] in bf16 or fp16 (in_dtype; what autocast feeds the conv), bias [C] fp32 or NULL, logits
+ * [B,C,h,w] in out_dtype (SF_F32 / SF_BF16 / SF_F16) -- the NCHW layout and dtypes sf_ce_onepass / sf_eval_hist read, so
+ * nothing is converted in between.  tcgen05 tensor cores with the accumulator in tensor memory, operands staged by TMA.
+ * Needs h*w % 8 == 0, K % 8 == 0, C <= 256 and 16-byte aligned x / weight; otherwise SF_ERR_UNSUPPORTED (fp32 inputs included:
+ * keep torch's conv for those).
+ */
+int sf_head_classifier(const void* x, const void* weight, const float* bias, void* logits, int in_dtype, int out_dtype,
+                       int B, int C, int K, int h, int w, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,7 +19,7 @@ SF_I64, SF_U8 = 0, 1
 SYMBOLS = (
     "sf_version", "sf_strerror", "sf_workspace_bytes", "sf_eval_hist", "sf_ce_forward",
     "sf_loss_finalize", "sf_focal_finalize", "sf_ce_backward", "sf_hist_pairs", "sf_accumulate_counts",
-    "sf_label_lut", "sf_eval_update", "sf_ce_onepass_supported", "sf_ce_onepass", "sf_ce_onepass_backward", "sf_dice_workspace_bytes", "sf_ce_dice_forward", "sf_dice_stats", "sf_dice_finalize", "sf_dice_coef", "sf_dice_backward",
+    "sf_label_lut", "sf_eval_update", "sf_head_classifier", "sf_ce_onepass_supported", "sf_ce_onepass", "sf_ce_onepass_backward", "sf_dice_workspace_bytes", "sf_ce_dice_forward", "sf_dice_stats", "sf_dice_finalize", "sf_dice_coef", "sf_dice_backward",
 )
 
 _lib = None
@@ -55,6 +55,8 @@ def lib() -> ctypes.CDLL:
         getattr(L, name).restype = i
     L.sf_eval_update.argtypes = [vp, i, vp, i, i, i, i, i, i, i, i, vp, vp, vp, vp, vp]
     L.sf_eval_update.restype = i
+    L.sf_head_classifier.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, i, vp]
+    L.sf_head_classifier.restype = i
     L.sf_hist_pairs.argtypes = [vp, i, vp, ll, i, vp, vp]
     L.sf_accumulate_counts.argtypes = [vp, vp, vp, vp, i, vp]
     L.sf_label_lut.argtypes = [vp, ll, vp, vp, i, vp]

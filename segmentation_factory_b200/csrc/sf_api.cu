@@ -71,6 +71,23 @@ int make_logits_tmap(CUtensorMap* map, const void* logits, int ldtype, int plane
     return r == CUDA_SUCCESS ? 0 : SF_ERR_DRIVER;
 }
 
+int make_tmap_generic(CUtensorMap* map, const void* base, int dtype, int rank, const unsigned long long* dims,
+                      const unsigned long long* strides, const unsigned* box, int swizzle128) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc || rank < 2 || rank > 3) return SF_ERR_DRIVER;
+    static thread_local bool ctx_bound = false;
+    if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; }
+    const CUtensorMapDataType dt = dtype == SF_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : dtype == SF_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    cuuint64_t gdim[3]; cuuint64_t gstr[2]; cuuint32_t bx[3]; cuuint32_t estr[3] = {1, 1, 1};
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; }
+    for (int i = 0; i < rank - 1; ++i) gstr[i] = strides[i];
+    const CUresult r = enc(map, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : SF_ERR_DRIVER;
+}
+
 }  // namespace sf
 
 extern "C" {
@@ -273,6 +290,12 @@ int sf_eval_update(const void* logits, int ldtype, const void* labels, int ydtyp
     const int rc = sf_eval_hist(logits, ldtype, labels, ydtype, B, C, h, w, H, W, ignore, counts, stream);
     if (rc != SF_OK) return rc;
     return sf::launch_accumulate_counts(counts, hist_f32, hist_i64, mat, C * C, stream);
+}
+
+int sf_head_classifier(const void* x, const void* weight, const float* bias, void* logits, int in_dtype, int out_dtype,
+                       int B, int C, int K, int h, int w, void* stream) {
+    if (h <= 0 || w <= 0) return SF_ERR_ARG;
+    return sf::launch_head_classifier(x, weight, bias, logits, in_dtype, out_dtype, B, C, K, (long long)h * w, stream);
 }
 
 int sf_hist_pairs(const void* a, int adtype, const long long* b, long long n, int C, unsigned long long* mat,

@@ -99,6 +99,12 @@ int launch_hist_pairs(const void* a, int adtype, const long long* b, long long n
 // 3-D tiled tensor map over logits viewed as [planes = B*C][h][w]; box = [box_c][box_h][box_w]
 int make_logits_tmap(CUtensorMap* map, const void* logits, int ldtype, int planes, int h, int w,
                      int box_c, int box_h, int box_w);
+// Tiled tensor map of rank 2 or 3 over 2-byte elements (bf16 / fp16): dims / box innermost first, strides in bytes for
+// dimensions 1.., optional 128-byte swizzle (sf_head_gemm.cu)
+int make_tmap_generic(CUtensorMap* map, const void* base, int dtype, int rank, const unsigned long long* dims,
+                      const unsigned long long* strides, const unsigned* box, int swizzle128);
+int launch_head_classifier(const void* x, const void* w, const float* bias, void* out, int in_dtype, int out_dtype,
+                           int B, int C, int K, long long N, void* stream);
 int sm_count();
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) costs ~1.5 us per call: do it once per kernel instantiation and device
