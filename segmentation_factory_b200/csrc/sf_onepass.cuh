@@ -51,6 +51,7 @@ struct OpParams {
     int B, h, w, H, W, ignore, label_u8;
     float thresh;
     int tiles_x, tiles_y;
+    long long lab_stride;                       // bytes between label rows (W << 3 for int64, W for uint8)
     int only_branch2;                           // BWD: unless sf_loss_state.branch == 2 only scale grad_acc into grad
     const float* grad_acc;                      // BWD + only_branch2: the fused walk's unscaled sums
     long long n_grad;                           //   B*C*h*w
@@ -96,9 +97,9 @@ __device__ __forceinline__ void op_onehot_sub2(int y, float2 (&a0)[NPA], float& 
 }
 
 // shared-memory `*p += v` when `on`, as ONE predicated instruction (no branch / reconvergence point in the row loop)
-__device__ __forceinline__ void red_shared_add_if(int* p, int v, bool on) {
+__device__ __forceinline__ void red_shared_add_if(uint32_t saddr, int v, bool on) {
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q red.shared.add.u32 [%0], %1;\n\t}"
-                 :: "r"(smem_u32(p)), "r"(v), "r"((int)on) : "memory");
+                 :: "r"(saddr), "r"(v), "r"((int)on) : "memory");
 }
 
 __device__ __forceinline__ float rcp_approx(float x) {
@@ -165,6 +166,7 @@ onepass_kernel(const __grid_constant__ CUtensorMap tmap, const OpParams p) {
     // grid = (tiles_x, tiles_y, B): tile coordinates come straight from the block index, so everything derived from them
     // (row range, base pointers of the label / loss streams) stays in uniform registers
     const int tid = threadIdx.x;
+    const uint32_t hist_sa = smem_u32(hist_s);                      // shared-window address, converted once
     const int txi = blockIdx.x, tyi = blockIdx.y, b = blockIdx.z;
     const int ia = tyi * TH, ib = min(ia + TH, p.h);
     const int ja = txi * G::TBW, jb = min(ja + G::TBW, p.w);
@@ -225,7 +227,6 @@ onepass_kernel(const __grid_constant__ CUtensorMap tmap, const OpParams p) {
     // inside the row loop, ~35 instructions per row).
     int nlo = -1; float nloss = 0.f;
     const char* labp = lab_base + ((size_t)(colok ? X : 0) << lab_shift);          // label of the next row to fetch
-    const size_t lab_stride = (size_t)p.W << lab_shift;
     float* lossp = loss_base + (colok ? X : 0);                     // FUSED: row being consumed (store); BWD: next row to fetch
     int rows_left = Yb - Ya;                                        // rows still to fetch; the row being consumed is one behind
     // No guard around the loads (a guard is one more branch per row): the pointers stop at the tile's last row, which is
@@ -235,7 +236,7 @@ onepass_kernel(const __grid_constant__ CUtensorMap tmap, const OpParams p) {
         if (bwd_has_loss) nloss = __ldg(lossp);
         --rows_left;
         if (rows_left > 0) {                                         // CTA-uniform
-            labp += lab_stride;
+            labp += p.lab_stride;
             if (!FUSED) lossp += p.W;
         }
     };
@@ -309,7 +310,7 @@ onepass_kernel(const __grid_constant__ CUtensorMap tmap, const OpParams p) {
 
     // per-thread loss statistics of the owned pixels (FUSED).  OHEM needs {n_valid, n_hard, sum_hard}; CE {n_valid, sum, sum_w}.
     float stat_a = 0.f, stat_b = 0.f;                               // OHEM: sum_hard, -        CE: sum_loss, sum_w
-    int cnt_valid = 0, cnt_hard = 0;
+    int cnts = 0;                                                   // n_valid | n_hard << 16 of this tile's owned pixels (<= 68 rows)
     int hrun_key = -1, hrun_cnt = 0;                                // confusion-matrix run of this thread's column
 
     // one row group u: top/bot = lerped logits of rows i0/i1, at/ab = gradient accumulators of rows i0/i1
@@ -405,8 +406,8 @@ onepass_kernel(const __grid_constant__ CUtensorMap tmap, const OpParams p) {
                         coef = keep ? wy : 0.f;
                         work = keep;
                         const bool ov = own && valid, ok = own && keep;
-                        cnt_valid += ov ? 1 : 0;
-                        if (OHEM) { stat_a += ok ? l : 0.f; cnt_hard += ok ? 1 : 0; }
+                        cnts += (ov ? 1 : 0) + ((OHEM && ok) ? 0x10000 : 0);
+                        if (OHEM) stat_a += ok ? l : 0.f;
                         else { stat_a += ov ? l : 0.f; stat_b += ov ? wy : 0.f; }
                         if (HIST) {
                             int idx = __ffs(~((bits_hi << CH) | bits_lo)) - 1;
@@ -429,7 +430,7 @@ onepass_kernel(const __grid_constant__ CUtensorMap tmap, const OpParams p) {
                             int key = valid ? lo * C + idx : -1;
                             key = own ? key : hrun_key;
                             const bool chg = key != hrun_key;
-                            red_shared_add_if(hist_s + max(hrun_key, 0), hrun_cnt, chg && hrun_key >= 0);
+                            red_shared_add_if(hist_sa + 4u * (uint32_t)max(hrun_key, 0), hrun_cnt, chg && hrun_key >= 0);
                             hrun_cnt = chg ? 1 : hrun_cnt + (own ? 1 : 0);
                             hrun_key = key;
                         }
@@ -451,7 +452,7 @@ onepass_kernel(const __grid_constant__ CUtensorMap tmap, const OpParams p) {
                 }
             } else if (FUSED && HIST) {
                 // a row in which the whole warp is ignored still ends this column's matrix run
-                red_shared_add_if(hist_s + max(hrun_key, 0), hrun_cnt, own && hrun_key >= 0);
+                red_shared_add_if(hist_sa + 4u * (uint32_t)max(hrun_key, 0), hrun_cnt, own && hrun_key >= 0);
                 hrun_key = own ? -1 : hrun_key;
             }
             if (FUSED && OHEM) {
@@ -496,7 +497,7 @@ onepass_kernel(const __grid_constant__ CUtensorMap tmap, const OpParams p) {
 
     if (FUSED) {
         if (HIST) {
-            if (hrun_key >= 0) atomicAdd(&hist_s[hrun_key], hrun_cnt);
+            red_shared_add_if(hist_sa + 4u * (uint32_t)max(hrun_key, 0), hrun_cnt, hrun_key >= 0);
             __syncthreads();
             for (int k = tid; k < C * C; k += kOpThreads) {
                 const int v = hist_s[k];
@@ -504,7 +505,7 @@ onepass_kernel(const __grid_constant__ CUtensorMap tmap, const OpParams p) {
             }
         }
         // per-CTA sums in a fixed order, then order-free integer atomics (Workspace::fx_*)
-        double v[4] = {(double)stat_a, (double)stat_b, (double)cnt_valid, (double)cnt_hard};
+        double v[4] = {(double)stat_a, (double)stat_b, (double)(cnts & 0xffff), (double)(cnts >> 16)};
         #pragma unroll
         for (int f = 0; f < 4; ++f) {
             #pragma unroll
@@ -541,6 +542,7 @@ inline int op_launch(const OnepassArgs& a) {
     p.grad = MODE == OP_FUSED ? (void*)a.grad_acc : a.grad_logits;
     p.B = a.B; p.h = a.h; p.w = a.w; p.H = a.H; p.W = a.W; p.ignore = a.ignore; p.label_u8 = a.ydtype == SF_U8;
     p.thresh = a.thresh; p.only_branch2 = a.only_branch2;
+    p.lab_stride = (long long)a.W << (a.ydtype == SF_U8 ? 0 : 3);
     p.grad_acc = a.grad_acc; p.n_grad = (long long)a.B * a.C * a.h * a.w;
     p.tiles_x = (a.w + G::TBW - 1) / G::TBW;
     p.tiles_y = (a.h + TH - 1) / TH;
