@@ -26,7 +26,6 @@ constexpr int kBfThreads = 128;                // label columns per tile; small 
 constexpr int kBfJL = kBfThreads / 4;          // gather lanes along j (>= owned columns per tile)
 constexpr int kBfTH = 8;                       // owned low-res rows per tile
 constexpr int kBfBH = kBfTH + 2;               // staged source rows: ia-1 .. ia+TH
-constexpr int kBfPrefetchRows = 3;             // L2 prefetch distance of the per-pixel streams, in label rows
 
 struct BfParams {
     const void* labels;
@@ -142,36 +141,49 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
     // ---- row walk state ----
     const int Ya = TP::first(ia - 1 < -1 ? -1 : ia - 1);
     const int Yb = ib >= p.h ? p.H : TP::first(ib);                // exclusive
-    // Prefetched inputs of the next row, fetched through running pointers so the
-    // row loop carries no 64-bit multiplies; `to_fetch` counts the rows still to fetch (the row being consumed is one behind).
+    // Prefetched inputs of the next row through running 64-bit pointers (base + 64-bit offset made ptxas rematerialise the
+    // address products in the row loop); no guard around the loads -- the pointers stop at the tile's last row, which is then
+    // read again, and idle columns read column 0 and are masked by `colok`.  The tile's lines of the per-pixel streams are
+    // pulled into L2 once, here, instead of three rows ahead inside the loop.
     int nlo = -1; float nlse = 0.f, nloss = 0.f, ncb = 0.f;
     const bool has_loss = branch != 0;
-    // one running pixel offset instead of three or four running pointers (register pressure: see emit_row's note)
-    long long pxo = ((long long)b * p.H + Ya) * p.W + (colok ? X : 0);
-    const float* loss_base = DICE ? p.coef_a : has_loss ? p.loss_px : p.lse_px;
-    int to_fetch = colok ? Yb - Ya : 0;                             // rows still to fetch; the row being consumed is one behind
     const int lab_shift = p.label_u8 ? 0 : 3;
-    const long long pf_px = (long long)kBfPrefetchRows * p.W;        // L2 prefetch distance in pixels
-    auto prefetch = [&]() {
-        if (to_fetch > 0) {
-            // the prefetch addresses are derived from the load addresses (base + pxo), not recomputed from pxo
-            const char* labp = reinterpret_cast<const char*>(p.labels) + (pxo << lab_shift);
-            const float* lsep = p.lse_px + pxo;
-            const float* lossp = loss_base + pxo;
-            nlo = p.label_u8 ? (int)__ldg(reinterpret_cast<const unsigned char*>(labp)) : __ldg(reinterpret_cast<const int*>(labp));
-            nlse = __ldg(lsep);
-            if (has_loss) nloss = __ldg(lossp);
-            if (DICE) ncb = __ldg(p.coef_b + pxo);
-            if (to_fetch > kBfPrefetchRows) {
-                // one row of work (~500 clk) does not cover a DRAM miss: measured 14 % long-scoreboard stall on the first use
-                // of these values.  Pull the lines of a few rows ahead into L2 (no registers involved).
-                prefetch_l2(labp + (pf_px << lab_shift));
-                prefetch_l2(lsep + pf_px);
-                if (has_loss) prefetch_l2(lossp + pf_px);
-                if (DICE) prefetch_l2(p.coef_b + pxo + pf_px);
-            }
+    const long long px0 = ((long long)b * p.H + Ya) * p.W;
+    const float* loss_base = DICE ? p.coef_a : has_loss ? p.loss_px : p.lse_px;
+    {
+        const int x0 = max(S * ja - S / 2, 0), x1 = min(S * ja - S / 2 + kBfThreads, p.W);
+        constexpr int LPR = kBfThreads * 8 / 128 + 1, LPR4 = kBfThreads * 4 / 128 + 1;
+        const char* lb = reinterpret_cast<const char*>(p.labels) + (px0 << lab_shift);
+        for (int i = tid; i < (Yb - Ya) * LPR; i += kBfThreads) {
+            const int r = i / LPR, l = i - r * LPR;
+            const long long px = (long long)r * p.W + min(x0 + ((l * 128) >> lab_shift), x1 - 1);
+            prefetch_l2(lb + (px << lab_shift));
         }
-        pxo += p.W; --to_fetch;
+        for (int i = tid; i < (Yb - Ya) * LPR4; i += kBfThreads) {
+            const int r = i / LPR4, l = i - r * LPR4;
+            const long long px = px0 + (long long)r * p.W + min(x0 + l * 32, x1 - 1);
+            prefetch_l2(p.lse_px + px);
+            if (has_loss) prefetch_l2(loss_base + px);
+            if (DICE) prefetch_l2(p.coef_b + px);
+        }
+    }
+    const long long pxs = px0 + (colok ? X : 0);
+    const char* labp = reinterpret_cast<const char*>(p.labels) + (pxs << lab_shift);
+    const long long lab_stride = (long long)p.W << lab_shift;
+    const float* lsep = p.lse_px + pxs;
+    const float* lossp = loss_base + pxs;
+    const float* cbp = DICE ? p.coef_b + pxs : nullptr;
+    int rows_left = Yb - Ya;                                        // rows still to fetch; the row being consumed is one behind
+    auto prefetch = [&]() {
+        nlo = p.label_u8 ? (int)__ldg(reinterpret_cast<const unsigned char*>(labp)) : __ldg(reinterpret_cast<const int*>(labp));
+        nlse = __ldg(lsep);
+        if (has_loss) nloss = __ldg(lossp);
+        if (DICE) ncb = __ldg(cbp);
+        --rows_left;
+        if (rows_left > 0) {                                         // CTA-uniform
+            labp += lab_stride; lsep += p.W; lossp += p.W;
+            if (DICE) cbp += p.W;
+        }
     };
     prefetch();
     const int ign = p.ignore;
@@ -252,10 +264,9 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
         #pragma unroll 1
         for (int r = 0; r < cnt; ++r, lh1 += lh1_step) {
             const int lo = nlo; const float lse = nlse, loss = nloss, cbv = ncb;
-            const bool alive = to_fetch >= 0;                        // prefetch() runs one row ahead
-            prefetch();
+            prefetch();                                              // runs one row ahead
             // valid label: 0 <= y < C, y != ignore (labels are read as their low 32 bits, see ld_label_lo32)
-            const bool valid = alive && (unsigned)lo < (unsigned)Ct && lo != ign;
+            const bool valid = colok && (unsigned)lo < (unsigned)Ct && lo != ign;
             float keep = 1.f;
             if (has_loss) keep = is_focal ? loss : (loss > kth ? 1.f : (loss == kth ? tie : 0.f));   // focal: loss_px holds d focal / d ce
             const float wy = cw_s[valid ? lo : 0];

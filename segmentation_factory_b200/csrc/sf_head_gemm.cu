@@ -12,9 +12,9 @@
 //   A = X^T: MN-major -- for a fixed k the 128 positions are contiguous in global memory.  TMA (SWIZZLE_128B) drops a
 //       [64 k][64 positions] box as 64 rows of 128 B; that IS the canonical MN-major SW128 layout (8-row groups 1024 B
 //       apart = SBO, the second 64-position half 8192 B further = LBO).
-//   B = W^T: K-major -- W is [C][K] with K contiguous.  TMA boxes of [8 classes][64 k] are one SW128 atom each (SBO = 1024 B);
-//       rows past C are zero-filled by TMA (partial boxes) or zeroed once at start (whole 8-row groups), so Cpad = the
-//       next multiple of 16 and the padded classes cost nothing but tensor-core time.
+//   B = W^T: K-major -- W is [C][K] with K contiguous.  TMA boxes of [8 | 16 | 32 classes][64 k] are SW128 atoms of 8 rows
+//       (SBO = 1024 B); rows past C are zero-filled by TMA (every box starts inside the tensor) or, below 16 classes, zeroed
+//       once at start, so Cpad = the next multiple of 16 and the padded classes cost nothing but tensor-core time.
 // Warp roles (320 threads, one persistent CTA per SM): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
 // warps 2..9 = epilogue (two warps per 32-lane TMEM quarter, each taking half of the class columns: tcgen05.ld, + bias,
 // convert, coalesced stores along n).  Two pipelines: shared-memory stages (full / empty mbarriers, tcgen05.commit frees a
@@ -45,6 +45,7 @@ struct HgParams {
     int stages;
     int tiles_per_img, total_tiles;
     int w_resident;                             // W stays in shared memory for the whole kernel
+    int wbox;                                   // class rows per W TMA box (8, 16 or 32)
 };
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
@@ -110,7 +111,11 @@ head_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     __shared__ float bias_s[256];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int wrows = (p.C + 7) / 8 * 8;         // classes covered by TMA boxes; [wrows, cpad) is zeroed once below
+    // Class rows covered by TMA boxes; every box starts inside the tensor, so TMA zero-fills the rows past C.  Only with
+    // fewer than 16 classes (8-row boxes) is there a whole 8-row group [wrows, cpad) no box writes: zeroed once below.
+    // (Fewer, larger boxes matter when W is streamed: 19 eight-row boxes per stage at 150 classes made the single
+    // producer thread the bottleneck.)
+    const int wrows = (p.C + p.wbox - 1) / p.wbox * p.wbox;
 
     if (tid == 0) {
         tma_prefetch_desc(&tmap_x);
@@ -150,7 +155,7 @@ head_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             if (p.w_resident) {
                 mbar_expect_tx(&w_bar, (uint32_t)(nkb * wrows * 128));
                 for (int kb = 0; kb < nkb; ++kb)
-                    for (int r = 0; r < wrows; r += 8) tma_load_2d(smem + kb * w_slice + r * 128, &tmap_w, &w_bar, kb * kHgBK, r);
+                    for (int r = 0; r < wrows; r += p.wbox) tma_load_2d(smem + kb * w_slice + r * 128, &tmap_w, &w_bar, kb * kHgBK, r);
             }
             int stage = 0; uint32_t phase = 0;
             for (int t = 0; t < n_tiles; ++t) {
@@ -163,7 +168,7 @@ head_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     tma_load_3d(xs, &tmap_x, &full_bar[stage], n0, kb * kHgBK, b);
                     tma_load_3d(xs + kHgXStage / 2, &tmap_x, &full_bar[stage], n0 + 64, kb * kHgBK, b);
                     if (!p.w_resident)
-                        for (int r = 0; r < wrows; r += 8) tma_load_2d(xs + kHgXStage + r * 128, &tmap_w, &full_bar[stage], kb * kHgBK, r);
+                        for (int r = 0; r < wrows; r += p.wbox) tma_load_2d(xs + kHgXStage + r * 128, &tmap_w, &full_bar[stage], kb * kHgBK, r);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -255,6 +260,7 @@ int launch_head_classifier(const void* x, const void* w, const float* bias, void
     HgParams p{};
     p.bias = bias; p.out = out; p.B = B; p.C = C; p.K = K; p.N = (int)N;
     p.cpad = (C + 15) / 16 * 16;
+    p.wbox = (C >= 32 && p.cpad % 32 == 0) ? 32 : (C >= 16 ? 16 : 8);
     const int nkb = (K + kHgBK - 1) / kHgBK;
     const int w_all = nkb * p.cpad * 128;
     p.w_resident = w_all <= 64 * 1024;
@@ -274,7 +280,7 @@ int launch_head_classifier(const void* x, const void* w, const float* bias, void
         if (rc != 0) return rc;
         const unsigned long long dw[2] = {(unsigned long long)K, (unsigned long long)C};
         const unsigned long long sw[1] = {(unsigned long long)K * 2};
-        const unsigned bw[2] = {(unsigned)kHgBK, 8};
+        const unsigned bw[2] = {(unsigned)kHgBK, (unsigned)p.wbox};
         rc = make_tmap_generic(&tw, w, in_dtype, 2, dw, sw, bw, 1);
         if (rc != 0) return rc;
     }
