@@ -59,6 +59,7 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmap, const FcParams p) {
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + kFcStages * G::STAGE_BYTES + p.hist_bytes);
     __shared__ double red_scratch[kFcThreads / 32];
     __shared__ float cw_s[256];
+    __shared__ uint64_t empty_bar[kFcStages];                       // consumer -> producer: "every warp is done with this stage"
 
     const int tid = threadIdx.x;
     const int tx = tid % kFcTW, sy = tid / kFcTW;
@@ -85,7 +86,7 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmap, const FcParams p) {
     if (tid < 256) cw_s[tid] = (p.class_w && tid < C) ? __ldg(p.class_w + tid) : 1.0f;
     if (tid == 0) {
         tma_prefetch_desc(&tmap);
-        for (int s = 0; s < kFcStages; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < kFcStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty_bar[s], kFcThreads / 32); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -405,8 +406,15 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmap, const FcParams p) {
             acc_loss += (double)tile_loss; acc_w += (double)tile_w; acc_hard += (double)tile_hard;
         }
 
-        __syncthreads();                                             // all threads are done with this stage
-        if (tid == 0 && n + kFcStages < n_items) issue(n + kFcStages);
+        // Release the stage warp by warp (as sf_forward_fast.cu does) instead of a CTA-wide barrier per item -- 0.8 stall cycles
+        // per issued instruction in the cfg-3 profile: only the producer thread waits until all 16 warps have left the item
+        // before its TMA overwrites the stage; the other warps run ahead into the next item, whose stage landed earlier.
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&empty_bar[slot]);
+        if (tid == 0 && n + kFcStages < n_items) {
+            mbar_wait(&empty_bar[slot], (uint32_t)phase);
+            issue(n + kFcStages);
+        }
     }
 
     if (DSTAT && cur_b >= 0) flush_bins(cur_b);
