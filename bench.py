@@ -41,12 +41,15 @@ def onepass_min_bytes_per_px(c, esz, lbytes, scale, ohem):
     return c * esz / (scale * scale) + c * 4.0 / (scale * scale) + lbytes + (4 if ohem else 0)
 
 
+STEP_SOURCES = ("sf_onepass.cuh", "sf_onepass.cu", "sf_onepass_f32.cu", "sf_common.cuh", "sf_fast.cuh", "sf_select.cu")
+
+
 def src_sha16():
-    """Hash of the kernel sources: ncu-derived numbers under profiles/ are only quoted when they match this build."""
+    """Hash of the sources of the kernels one bench step launches (walk, finalize, backward): ncu-derived numbers under
+    profiles/ are only quoted when they were captured on exactly these sources."""
     h = hashlib.sha256()
-    for name in sorted(os.listdir(CSRC)):
-        if name.endswith((".cu", ".cuh", ".h")):
-            h.update(open(os.path.join(CSRC, name), "rb").read())
+    for name in STEP_SOURCES:
+        h.update(open(os.path.join(CSRC, name), "rb").read())
     return h.hexdigest()[:16]
 
 

@@ -405,6 +405,8 @@ static int bf_classes(const BwdArgs& a, int s) {
     switch (a.C) {
         case 19: return bf_scale<LT, 19, false>(a, s);
         case 21: return bf_scale<LT, 21, false>(a, s);
+        case 9: return bf_scale<LT, 9, false>(a, s);
+        case 2: return bf_scale<LT, 2, false>(a, s);
         default: return a.C > 24 ? bf_scale<LT, 16, true>(a, s) : -1000;   // many classes: 16-class chunks
     }
 }

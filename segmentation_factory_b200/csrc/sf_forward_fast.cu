@@ -557,6 +557,8 @@ static int ff_classes(const FwdArgs& a, int s) {
     switch (a.C) {
         case 19: return ff_scale<LT, 19>(a, s);
         case 21: return ff_scale<LT, 21>(a, s);
+        case 9: return ff_scale<LT, 9>(a, s);                        // Synapse (train_gpu.py:48-49)
+        case 2: return ff_scale<LT, 2>(a, s);                        // Kvasir
         default: return -1000;
     }
 }

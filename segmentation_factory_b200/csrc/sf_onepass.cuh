@@ -596,9 +596,11 @@ inline int op_mode(const OnepassArgs& a) {
         default: break;
     }
 #endif
-    // 16-row tiles recompute fewer halo rows (17/16 vs 9/8 of the pixels) but need enough tiles to fill the GPU
+    // 16-row tiles recompute fewer halo rows (17/16 vs 9/8 of the pixels) but need enough tiles to fill the GPU and must
+    // leave room for kOpMinB CTAs per SM in shared memory
     const long long tiles16 = (long long)a.B * ((a.h + 15) / 16) * ((a.w + OpGeom<LT, C, S, 16>::TBW - 1) / OpGeom<LT, C, S, 16>::TBW);
-    if (a.h >= 18 && tiles16 >= 4LL * kOpMinB * sm_count()) return op_mode2<LT, C, S, 16, kOpMinB, 1>(a);
+    constexpr bool fits16 = OpGeom<LT, C, S, 16>::smem(true) * kOpMinB <= 227 * 1024;   // e.g. C = 21 fp32: 78 KB -> only two CTAs per SM
+    if (fits16 && a.h >= 18 && tiles16 >= 4LL * kOpMinB * sm_count()) return op_mode2<LT, C, S, 16, kOpMinB, 1>(a);
     return op_mode2<LT, C, S, 8, kOpMinB, 1>(a);
 }
 template <typename LT, int C>
