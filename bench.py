@@ -521,7 +521,7 @@ def main():
                     "collective": "one all_reduce(int64[C*C+2]) after the last step, inside the timed region" if world > 1 else "none",
                     "src_sha16": src_sha16()},
             "clocks": clocks, "e2e": e2e, "e2e_u8_ingest": e2e_u8,
-            "gpu_launches": (4 if onepass else 3) * args.steps, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": 3 * args.steps, "roofline": roofline, "cpu_baseline": cpu,
             "torch_cpu_reference": torch_cpu,
         }
         if reduce_leg:

@@ -36,8 +36,8 @@ with open(out + ".md", "w") as f:
             return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
         tb = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
         f.write(f"| dram read+write per launch | {tb/1e6:.1f} | MB |\n\n")
-        short = ("walk" if "onepass_kernel" in name and ", 0, " in name.split("onepass_kernel")[1][:40] else
-                 "backward" if "onepass_kernel" in name else "head_gemm" if "head_gemm" in name else
+        op_mode = name.split("<")[1].split(">")[0].split(",")[6].strip() if "onepass_kernel<" in name else ""   # 7th template argument: OP_FUSED / OP_BWD
+        short = ("walk" if op_mode == "0" else "backward" if op_mode == "1" else "head_gemm" if "head_gemm" in name else
                  "fwd" if "fwd" in name else "bwd" if "bwd" in name else "finalize" if "finalize" in name else name[:20])
         traffic[short] = tb
 json.dump(traffic, open(out + "_traffic.json", "w"), indent=1)
