@@ -55,6 +55,7 @@ struct OpParams {
     int only_branch2;                           // BWD: unless sf_loss_state.branch == 2 only scale grad_acc into grad
     const float* grad_acc;                      // BWD + only_branch2: the fused walk's unscaled sums
     long long n_grad;                           //   B*C*h*w
+    int C, th, n_chunks, ohem;                  // sf_onepass_chunk.cuh: runtime class count, tile height, 16-class chunks, OHEM on
 };
 
 // TH = owned low-res rows per tile (8 or 16); the box stages rows ia-1 .. ia+TH
