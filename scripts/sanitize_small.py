@@ -36,6 +36,11 @@ run(1, 40, 32, 80, 128, 320, torch.float32, "ce")    # chunk kernels
 run(1, 7, 20, 33, 61, 100)                           # generic, non-integer, no TMA (odd pitch)
 run(1, 5, 24, 32, 50, 70, torch.float16)             # generic with TMA
 run(1, 19, 64, 96, 64, 96)                           # same-size streaming kernels
+os.environ["SF_ONEPASS_CHUNK"] = "1"
+run(1, 40, 24, 72, 96, 288, torch.float32, "ce")     # many-class one-pass walk (opt-in): tail chunk of 8, narrow tiles
+run(1, 150, 12, 64, 48, 256, torch.bfloat16)         # ... OHEM, bf16, wide tiles
+run(1, 40, 24, 72, 96, 288, late=True)               # ... speculation fails: two-pass re-walk in backward mode
+os.environ["SF_ONEPASS_CHUNK"] = "0"
 os.environ["SF_NO_FAST"] = "1"
 run(1, 19, 32, 80, 128, 320)                         # generic kernels on a fast-path shape (top-k select may fire)
 os.environ["SF_NO_FAST"] = "0"

@@ -24,9 +24,8 @@ template <typename LT>
 __global__ void __launch_bounds__(256)
 onepass_scale_kernel(const float* __restrict__ acc, LT* __restrict__ out, long long n, const float* __restrict__ grad_out,
                      const Workspace* __restrict__ ws) {
-    if (ws->state.branch == 2) return;
-    const float s = (grad_out ? __ldg(grad_out) : 1.0f) * ws->state.inv_denom;
-    scale_slice<LT>(acc, out, n, s, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
+    scale_slice<LT, 16>(acc, out, n, grad_out, &ws->state, (long long)blockIdx.x * blockDim.x + threadIdx.x,
+                        (long long)gridDim.x * blockDim.x);
 }
 
 bool onepass_supported(int ldtype, const void* logits, int C, int h, int w, int H, int W) {

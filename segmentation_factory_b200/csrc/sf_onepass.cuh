@@ -109,31 +109,60 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return y;
 }
 
-// out[i] = acc[i] * s over a grid-strided slice (this CTA's share); eight 128-bit loads in flight per thread
+// out[i] = acc[i] * (grad_out * inv_denom) over a grid-strided slice (this CTA's share), unless the loss state says branch 2
+// (top-k): then nothing is written and false is returned.  A thread's share is small (~18 float4 at the bench shape with one
+// slice per tile CTA), so the time of a CTA is a latency chain, not bandwidth: all loads of a batch of U are issued BEFORE
+// the state is read (they are wasted on branch 2, which re-walks anyway), and the tail is one predicated batch instead of
+// one load at a time.
 template <typename LT>
-__device__ __forceinline__ void scale_slice(const float* __restrict__ acc, LT* __restrict__ out, long long n, float s,
+__device__ __forceinline__ void scale_put4(LT* o, float4 v, float s) {
+    if (sizeof(LT) == 4) {
+        *reinterpret_cast<float4*>(o) = make_float4(v.x * s, v.y * s, v.z * s, v.w * s);
+    } else {
+        unsigned lo, hi;                                             // 4 x 16 bit in one 8-byte store
+        if (Logit<LT>::code == SF_BF16) {
+            const __nv_bfloat162 a = __floats2bfloat162_rn(v.x * s, v.y * s), b = __floats2bfloat162_rn(v.z * s, v.w * s);
+            lo = *reinterpret_cast<const unsigned*>(&a); hi = *reinterpret_cast<const unsigned*>(&b);
+        } else {
+            const __half2 a = __floats2half2_rn(v.x * s, v.y * s), b = __floats2half2_rn(v.z * s, v.w * s);
+            lo = *reinterpret_cast<const unsigned*>(&a); hi = *reinterpret_cast<const unsigned*>(&b);
+        }
+        *reinterpret_cast<uint2*>(o) = make_uint2(lo, hi);
+    }
+}
+
+template <typename LT, int U>
+__device__ __forceinline__ bool scale_slice(const float* __restrict__ acc, LT* __restrict__ out, long long n,
+                                            const float* __restrict__ grad_out, const sf_loss_state* __restrict__ stp,
                                             long long first, long long stride) {
     const bool vec = (((uintptr_t)acc | (uintptr_t)out) & 15) == 0;
     const long long n4 = vec ? n >> 2 : 0;
     const float4* a4 = reinterpret_cast<const float4*>(acc);
-    auto put = [&](long long i, float4 v) {
-        LT* o = out + 4 * i;
-        if (sizeof(LT) == 4) {
-            *reinterpret_cast<float4*>(o) = make_float4(v.x * s, v.y * s, v.z * s, v.w * s);
-        } else {
-            Logit<LT>::st(o, v.x * s); Logit<LT>::st(o + 1, v.y * s); Logit<LT>::st(o + 2, v.z * s); Logit<LT>::st(o + 3, v.w * s);
-        }
-    };
-    long long i = first;
-    for (; i + 7 * stride < n4; i += 8 * stride) {
-        float4 v[8];
-        #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = __ldcs(a4 + i + u * stride);
-        #pragma unroll
-        for (int u = 0; u < 8; ++u) put(i + u * stride, v[u]);
+    float4 v[U];
+    #pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const long long i = first + u * stride;
+        if (i < n4) v[u] = __ldcs(a4 + i);
     }
-    for (; i < n4; i += stride) put(i, __ldcs(a4 + i));
+    if (stp->branch == 2) return false;
+    const float s = (grad_out ? __ldg(grad_out) : 1.0f) * stp->inv_denom;
+    long long i0 = first;
+    while (true) {
+        #pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * stride;
+            if (i < n4) scale_put4<LT>(out + 4 * i, v[u], s);
+        }
+        i0 += U * stride;
+        if (i0 >= n4) break;
+        #pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * stride;
+            if (i < n4) v[u] = __ldcs(a4 + i);
+        }
+    }
     for (long long j = 4 * n4 + first; j < n; j += stride) Logit<LT>::st(out + j, acc[j] * s);
+    return true;
 }
 
 template <typename LT, int C, int S, int TH, int MINB, int UNR, int MODE, bool OHEM, bool HIST>
@@ -155,13 +184,13 @@ onepass_kernel(const __grid_constant__ CUtensorMap tmap, const OpParams p) {
     __shared__ double red_s[kOpThreads / 32][5];
 
     const sf_loss_state* stp = &p.ws->state;
-    if (!FUSED && p.only_branch2 && stp->branch != 2) {
-        // the speculative gradient sums of the fused walk stand: grad = acc * grad_out / denom, this CTA's slice
+    if (!FUSED && p.only_branch2) {
+        // unless the loss took the top-k branch the speculative gradient sums of the fused walk stand:
+        // grad = acc * grad_out / denom, this CTA's slice
         const long long cta = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
         const long long n_cta = (long long)gridDim.x * gridDim.y * gridDim.z;
-        const float sc = (p.grad_out ? __ldg(p.grad_out) : 1.0f) * stp->inv_denom;
-        scale_slice<LT>(p.grad_acc, reinterpret_cast<LT*>(p.grad), p.n_grad, sc, cta * kOpThreads + threadIdx.x, n_cta * kOpThreads);
-        return;
+        if (scale_slice<LT, 20>(p.grad_acc, reinterpret_cast<LT*>(p.grad), p.n_grad, p.grad_out, stp,
+                                cta * kOpThreads + threadIdx.x, n_cta * kOpThreads)) return;
     }
 
     // grid = (tiles_x, tiles_y, B): tile coordinates come straight from the block index, so everything derived from them

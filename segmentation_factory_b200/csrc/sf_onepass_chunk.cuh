@@ -65,13 +65,12 @@ onepass_chunk_kernel(const __grid_constant__ CUtensorMap tmap, const OpParams p)
     __shared__ double red_s[NT / 32][4];
 
     const sf_loss_state* stp = &p.ws->state;
-    if (!FUSED && p.only_branch2 && stp->branch != 2) {
-        // the speculative gradient sums of the fused walk stand: grad = acc * grad_out / denom, this CTA's slice
+    if (!FUSED && p.only_branch2) {
+        // unless the loss took the top-k branch the speculative gradient sums of the fused walk stand
         const long long cta = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
         const long long n_cta = (long long)gridDim.x * gridDim.y * gridDim.z;
-        const float sc = (p.grad_out ? __ldg(p.grad_out) : 1.0f) * stp->inv_denom;
-        scale_slice<LT>(p.grad_acc, reinterpret_cast<LT*>(p.grad), p.n_grad, sc, cta * NT + threadIdx.x, n_cta * NT);
-        return;
+        if (scale_slice<LT, 16>(p.grad_acc, reinterpret_cast<LT*>(p.grad), p.n_grad, p.grad_out, stp,
+                                cta * NT + threadIdx.x, n_cta * NT)) return;
     }
 
     const int tid = threadIdx.x, lane = tid & 31;
