@@ -17,7 +17,8 @@
 //       once at start, so Cpad = the next multiple of 16 and the padded classes cost nothing but tensor-core time.
 // Warp roles (320 threads, one persistent CTA per SM): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
 // warps 2..9 = epilogue (two warps per 32-lane TMEM quarter, each taking half of the class columns: tcgen05.ld, + bias,
-// convert, coalesced stores along n).  Two pipelines: shared-memory stages (full / empty mbarriers, tcgen05.commit frees a
+// convert, stage [16 classes][32 positions] in shared memory, one TMA store per group -- the tensor map clips the ragged
+// last tile and the classes past C).  Two pipelines: shared-memory stages (full / empty mbarriers, tcgen05.commit frees a
 // stage) and a double-buffered TMEM accumulator (tmem_full / tmem_empty), so the epilogue of tile i overlaps the loads and
 // MMAs of tile i + 1.  When W (cpad x K) fits in 64 KB it is loaded ONCE per CTA and stays resident (the usual case:
 // 19..21 classes); otherwise its 64-k slices travel with the X stages.
@@ -53,6 +54,15 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// shared memory -> global, tile mode; completion is tracked by the issuing thread's bulk async-groups
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {       // arrives on `bar` when every MMA issued so far has finished
@@ -97,7 +107,8 @@ template <> __device__ __forceinline__ void hg_store<__half>(__half* p, float v)
 
 template <bool BF16, typename OT>
 __global__ void __launch_bounds__(kHgThreads, 1)
-head_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const HgParams p) {
+head_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                 const __grid_constant__ CUtensorMap tmap_o, const HgParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // carve (all 1024-byte aligned, SWIZZLE_128B atoms): resident W [nkb][cpad rows x 128 B] | [stages] x { X: 16 KB (+ a W slice) }
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -109,6 +120,7 @@ head_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     __shared__ uint64_t full_bar[12], empty_bar[12], tmem_full[2], tmem_empty[2], w_bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ float bias_s[256];
+    __shared__ __align__(128) OT out_stage[kHgEpiWarps][2][16 * 32];   // per epilogue warp: two [16 classes][32 positions] boxes
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // Class rows covered by TMA boxes; every box starts inside the tensor, so TMA zero-fills the rows past C.  Only with
@@ -120,6 +132,7 @@ head_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     if (tid == 0) {
         tma_prefetch_desc(&tmap_x);
         tma_prefetch_desc(&tmap_w);
+        tma_prefetch_desc(&tmap_o);
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], kHgEpiWarps); }
         mbar_init(&w_bar, 1);
@@ -210,32 +223,35 @@ head_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         // ===== epilogue: warps 2..9; warp w reads TMEM lanes 32 * (w % 4) .. + 32 and every second 16-column group =====
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
-        const int row = q * 32 + lane;                            // position within the tile
-        OT* outp = reinterpret_cast<OT*>(p.out);
+        int sb = 0;                                                 // staging buffer of the next group
         for (int t = 0; t < n_tiles; ++t) {
             const int tile = blockIdx.x + t * gridDim.x;
             const int b = tile / p.tiles_per_img, n0 = (tile % p.tiles_per_img) * kHgBM;
             const int acc = t & 1;
             mbar_wait(&tmem_full[acc], (uint32_t)((t >> 1) & 1));
             tc_fence_after();
-            const int n = n0 + row;
-            const bool ok = n < p.N;
             for (int c0 = half * 16; c0 < p.C; c0 += 32) {
                 float v[16];
                 tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.cpad + c0), v);
-                if (ok) {
-                    OT* o = outp + ((long long)b * p.C + c0) * p.N + n;      // a warp covers 32 consecutive n: coalesced
-                    #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        if (c0 + i < p.C) hg_store<OT>(o, v[i] + bias_s[c0 + i]);
-                        o += p.N;
-                    }
+                // the store issued two groups ago has finished READING this staging buffer
+                if (lane == 0) tma_store_wait_read<1>();
+                __syncwarp();
+                OT* sbuf = out_stage[warp - 2][sb];
+                #pragma unroll
+                for (int i = 0; i < 16; ++i) hg_store<OT>(sbuf + i * 32 + lane, v[i] + bias_s[c0 + i]);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes visible to the TMA (async proxy)
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_3d(&tmap_o, sbuf, n0 + q * 32, c0, b);       // rows n >= N and classes >= C are clipped by the map
+                    tma_store_commit();
                 }
+                sb ^= 1;
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
+        if (lane == 0) tma_store_wait_all();                        // shared memory must outlive the last stores
     }
 
     tc_fence_before();
@@ -266,12 +282,15 @@ int launch_head_classifier(const void* x, const void* w, const float* bias, void
     p.w_resident = w_all <= 64 * 1024;
     const int stage_bytes = kHgXStage + (p.w_resident ? 0 : p.cpad * 128);
     const int w_res_bytes = p.w_resident ? w_all : 0;
-    p.stages = std::min(12, std::max(2, (208 * 1024 - w_res_bytes) / stage_bytes));
+    if ((uintptr_t)out % 16) return SF_ERR_UNSUPPORTED;                             // TMA store: 16-byte aligned rows
+    const int osz = out_dtype == SF_F32 ? 4 : 2;
+    const int out_stage_bytes = kHgEpiWarps * 2 * 16 * 32 * osz;                   // static shared memory of the epilogue
+    p.stages = std::min(12, std::max(2, (208 * 1024 - out_stage_bytes - w_res_bytes) / stage_bytes));
     p.tiles_per_img = (int)((N + kHgBM - 1) / kHgBM);
     const long long total = (long long)B * p.tiles_per_img;
     if (total >= (1LL << 31)) return SF_ERR_SHAPE;
     p.total_tiles = (int)total;
-    CUtensorMap tx{}, tw{};
+    CUtensorMap tx{}, tw{}, to{};
     {
         const unsigned long long dims[3] = {(unsigned long long)N, (unsigned long long)K, (unsigned long long)B};
         const unsigned long long strides[2] = {(unsigned long long)N * 2, (unsigned long long)N * K * 2};
@@ -283,6 +302,12 @@ int launch_head_classifier(const void* x, const void* w, const float* bias, void
         const unsigned bw[2] = {(unsigned)kHgBK, (unsigned)p.wbox};
         rc = make_tmap_generic(&tw, w, in_dtype, 2, dw, sw, bw, 1);
         if (rc != 0) return rc;
+        // logits [B][C][N]: the epilogue stores [16 classes][32 positions] boxes
+        const unsigned long long dout[3] = {(unsigned long long)N, (unsigned long long)C, (unsigned long long)B};
+        const unsigned long long sout[2] = {(unsigned long long)N * osz, (unsigned long long)N * C * osz};
+        const unsigned bo[3] = {32, 16, 1};
+        rc = make_tmap_generic(&to, out, out_dtype, 3, dout, sout, bo, /*swizzle128=*/0);
+        if (rc != 0) return rc;
     }
     const size_t smem = (size_t)w_res_bytes + (size_t)p.stages * stage_bytes + 1024;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -292,7 +317,7 @@ int launch_head_classifier(const void* x, const void* w, const float* bias, void
         static SmemLimitOnce once;                                                               \
         const cudaError_t e = set_smem_limit_once(head_gemm_kernel<BF, OT>, smem, once);         \
         if (e != cudaSuccess) return (int)e;                                                     \
-        head_gemm_kernel<BF, OT><<<grid, kHgThreads, smem, st>>>(tx, tw, p);                     \
+        head_gemm_kernel<BF, OT><<<grid, kHgThreads, smem, st>>>(tx, tw, to, p);                     \
     } while (0)
     if (in_dtype == SF_BF16) {
         if (out_dtype == SF_F32) SF_HG_LAUNCH(true, float);
