@@ -233,8 +233,10 @@ int sf_accumulate_counts(unsigned long long* counts, float* hist_f32, long long*
 
 /*
  * engine.py:90-91 for one batch in ONE call: sf_eval_hist into `counts` (device scratch of C*C, zero on entry, zero again on
- * return) followed by sf_accumulate_counts into the caller's accumulators.  Same kernels, one crossing of the language
- * boundary: at validation batch size 1 the host side of two calls costs more than the 17 us of GPU work per image.
+ * return) followed by sf_accumulate_counts into the caller's accumulators.  One crossing of the language boundary: at
+ * validation batch size 1 the host side of two calls costs more than the 17 us of GPU work per image.  Where the integer-scale
+ * kernel covers the shape (C in {2, 9, 19, 21}, scale 4 / 8) it is also ONE launch: the kernel's last CTA (atomic ticket kept
+ * in bits 48..63 of counts[0] while the kernel runs -- a call counts fewer than 2^40 pixels) performs the accumulation.
  */
 int sf_eval_update(const void* logits, int ldtype, const void* labels, int ydtype,
                    int B, int C, int h, int w, int H, int W, int ignore,

@@ -287,8 +287,15 @@ int sf_accumulate_counts(unsigned long long* counts, float* hist_f32, long long*
 
 int sf_eval_update(const void* logits, int ldtype, const void* labels, int ydtype, int B, int C, int h, int w, int H, int W,
                    int ignore, unsigned long long* counts, float* hist_f32, long long* hist_i64, long long* mat, void* stream) {
-    const int rc = sf_eval_hist(logits, ldtype, labels, ydtype, B, C, h, w, H, W, ignore, counts, stream);
-    if (rc != SF_OK) return rc;
+    if (!counts) return SF_ERR_ARG;
+    sf::FwdArgs a{};
+    a.logits = logits; a.ldtype = ldtype; a.labels = labels; a.ydtype = ydtype;
+    a.B = B; a.C = C; a.h = h; a.w = w; a.H = H; a.W = W; a.ignore = ignore;
+    a.hist = counts; a.stream = stream; a.softmax = false; a.force_no_tma = sf::env_no_tma();
+    int folded = 0;                                                 // set when the kernel's last CTA did the accumulation itself
+    a.fold_f32 = hist_f32; a.fold_i64 = hist_i64; a.fold_mat = mat; a.folded_out = &folded;
+    const int rc = sf::launch_forward(a);
+    if (rc != SF_OK || folded) return rc;
     return sf::launch_accumulate_counts(counts, hist_f32, hist_i64, mat, C * C, stream);
 }
 

@@ -34,6 +34,8 @@ struct FfParams {
     float thresh;
     int tiles_x, tiles_y, total_tiles;
     DiceArgs dice;                                                  // MODE >= 2 (sf_dice.cu)
+    float* fold_f32; long long* fold_i64; long long* fold_mat;      // FF_ARGMAX + fold: the per-call bookkeeping of sf_eval_update
+    int fold;
 };
 
 enum { FF_ARGMAX = 0, FF_SOFTMAX = 1, FF_DICE_STATS = 2, FF_DICE_COEF = 3, FF_SOFTMAX_STATS = 4, FF_SOFTMAX_NOHIST = 5 };
@@ -486,6 +488,27 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
             const int v = hist_s[k];
             if (v) atomicAdd(p.hist + k, (unsigned long long)v);
         }
+        if (MODE == FF_ARGMAX && p.fold) {
+            // Per-call bookkeeping of Metrics / ConfusionMatrix in the LAST CTA instead of a second launch.  The ticket lives in
+            // bits 48..63 of hist[0] (a call counts < 2^40 pixels, the grid has <= 1024 CTAs), so no extra caller memory is
+            // needed and the scratch matrix is left zeroed as sf_accumulate_counts leaves it.
+            __shared__ bool last_cta;
+            __threadfence();                                         // this CTA's counts before its ticket
+            __syncthreads();
+            if (tid == 0) last_cta = (atomicAdd(p.hist, 1ull << 48) >> 48) == (unsigned long long)(gridDim.x - 1);
+            __syncthreads();
+            if (last_cta) {
+                __threadfence();
+                for (int k = tid; k < C * C; k += kFfThreads) {
+                    unsigned long long c = __ldcg(p.hist + k);
+                    if (k == 0) c &= (1ull << 48) - 1ull;
+                    if (p.fold_f32) p.fold_f32[k] = __fadd_rn(p.fold_f32[k], __ull2float_rn(c));   // torch: float32 += int64
+                    if (p.fold_i64) p.fold_i64[k] += (long long)c;
+                    if (p.fold_mat) p.fold_mat[k] += (long long)c;
+                    p.hist[k] = 0ull;
+                }
+            }
+        }
     }
     if (SOFTMAX) {
         const double r0d = block_sum<kFfThreads>(acc_loss, red_scratch);
@@ -512,6 +535,8 @@ static int ff_launch(const FwdArgs& a) {
     p.ws = reinterpret_cast<Workspace*>(a.ws);
     p.B = a.B; p.h = a.h; p.w = a.w; p.H = a.H; p.W = a.W; p.ignore = a.ignore; p.label_u8 = a.ydtype == SF_U8;
     p.thresh = a.thresh; p.dice = a.dice;
+    p.fold_f32 = a.fold_f32; p.fold_i64 = a.fold_i64; p.fold_mat = a.fold_mat;
+    p.fold = MODE == FF_ARGMAX && a.folded_out != nullptr && a.hist != nullptr;
     p.tiles_x = (a.W + kFfTW - 1) / kFfTW;
     p.tiles_y = (a.h + 1 + G::NGT - 1) / G::NGT;
     const long long total = (long long)a.B * p.tiles_x * p.tiles_y;
@@ -533,7 +558,9 @@ static int ff_launch(const FwdArgs& a) {
     const int per_sm = gm ? std::max(1, atoi(gm)) : 2;
     const int grid = (int)std::min<long long>(total, std::min(kMaxCtas, per_sm * sm_count()));
     k<<<grid, kFfThreads, smem, reinterpret_cast<cudaStream_t>(a.stream)>>>(tmap, p);
-    return (int)cudaGetLastError();
+    const int lrc = (int)cudaGetLastError();
+    if (lrc == 0 && p.fold) *a.folded_out = 1;
+    return lrc;
 }
 
 template <typename LT, int C, int S>

@@ -34,6 +34,9 @@ struct FwdArgs {
     bool force_no_tma;     // SF_NO_TMA=1 in the environment (debug / A-B measurement)
     int dice_mode;         // DICE_OFF: the CE / argmax forward
     DiceArgs dice;
+    // sf_eval_update: a kernel that can do so folds `hist_f32 += hist; hist_i64 += hist; mat += hist; hist = 0` into its last
+    // CTA and sets *folded_out = 1 (host side, at launch); otherwise the caller runs launch_accumulate_counts afterwards
+    float* fold_f32; long long* fold_i64; long long* fold_mat; int* folded_out;
 };
 int launch_forward(const FwdArgs& a);
 int launch_forward_fast(const FwdArgs& a);    // -1000: shape not covered by the integer-scale specialisation
