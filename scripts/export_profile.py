@@ -40,5 +40,11 @@ with open(out + ".md", "w") as f:
         short = ("walk" if op_mode == "0" else "backward" if op_mode == "1" else "head_gemm" if "head_gemm" in name else
                  "fwd" if "fwd" in name else "bwd" if "bwd" in name else "finalize" if "finalize" in name else name[:20])
         traffic[short] = tb
+if "walk" in traffic:                                   # the bench step: stamp the kernel sources the capture ran on (bench.py checks it)
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import src_sha16
+    traffic["src_sha16"] = src_sha16()
+    traffic["source"] = "ncu --set full --clock-control none, one step of scripts/prof_onepass.py early"
 json.dump(traffic, open(out + "_traffic.json", "w"), indent=1)
 print("wrote", out + ".md/.csv/_traffic.json", traffic)

@@ -56,6 +56,7 @@ struct OpParams {
     const float* grad_acc;                      // BWD + only_branch2: the fused walk's unscaled sums
     long long n_grad;                           //   B*C*h*w
     int C, th, n_chunks, ohem;                  // sf_onepass_chunk.cuh: runtime class count, tile height, 16-class chunks, OHEM on
+    int xchg;                                   // FUSED: boundary rows are exchanged (two float atomics) instead of recomputed
 };
 
 // TH = owned low-res rows per tile (8 or 16); the box stages rows ia-1 .. ia+TH
@@ -229,7 +230,11 @@ onepass_kernel(const __grid_constant__ CUtensorMap tmap, const OpParams p) {
     const float2 l2e2 = splat(kLog2e);
 
     // ---- per-pixel streams (label, loss_px): one 32-bit pixel offset `off` against per-tile base pointers ----
-    const int Ya = TP::first(ia - 1 < -1 ? -1 : ia - 1);
+    // First group walked.  Halo mode: ia - 1, recomputed only for its lower vertical part into row ia.  Exchange mode (FUSED,
+    // p.xchg): ia -- the tile above adds its lower part of row ia itself, and this tile adds its own into row ib.
+    const bool xchg = FUSED && p.xchg != 0;
+    const int u0 = (xchg && ia > 0) ? ia : ia - 1;
+    const int Ya = TP::first(u0 < -1 ? -1 : u0);
     const int Yb = ib >= p.h ? p.H : TP::first(ib);                // exclusive
     const int lab_shift = p.label_u8 ? 0 : 3;
     const long long base_px = ((long long)b * p.H + Ya) * p.W;
@@ -292,7 +297,7 @@ onepass_kernel(const __grid_constant__ CUtensorMap tmap, const OpParams p) {
 
     int ecount = 0;
     // emit the finished source row i held in `acc`, then clear it.  Called uniformly by all threads.
-    auto emit_row = [&](int i, float2 (&acc)[NPA], float& accl) {
+    auto emit_row = [&](int i, float2 (&acc)[NPA], float& accl, bool shared_row) {
         if (i >= ia) {
             float* buf = Rbuf + (ecount & 1) * C * kOpThreads;
             ++ecount;
@@ -327,8 +332,14 @@ onepass_kernel(const __grid_constant__ CUtensorMap tmap, const OpParams p) {
                             sum = fmaf(v.z, wgt[d4 + 2], sum); sum = fmaf(v.w, wgt[d4 + 3], sum);
                         }
                         const long long o = go + (long long)k * G::KQ * p.h * p.w;
-                        if (FUSED) reinterpret_cast<float*>(p.grad)[o] = sum;
-                        else Logit<LT>::st(reinterpret_cast<LT*>(p.grad) + o, sum);
+                        if (FUSED) {
+                            // a row shared with the neighbouring tile has exactly two addends (this tile's part and the
+                            // neighbour's) on a zeroed element: float atomics in either order give the same bits
+                            if (shared_row) atomicAdd(reinterpret_cast<float*>(p.grad) + o, sum);
+                            else reinterpret_cast<float*>(p.grad)[o] = sum;
+                        } else {
+                            Logit<LT>::st(reinterpret_cast<LT*>(p.grad) + o, sum);
+                        }
                     }
                 }
             }
@@ -501,8 +512,8 @@ onepass_kernel(const __grid_constant__ CUtensorMap tmap, const OpParams p) {
     __syncthreads();
     mbar_wait(bar, 0);
 
-    // ---- walk groups u = ia-1 .. ib-1, two per iteration with swapped roles (no register copies) ----
-    int u = ia - 1;
+    // ---- walk groups u = u0 .. ib-1, two per iteration with swapped roles (no register copies) ----
+    int u = u0;
     {
         const int i0 = max(u, 0), i1 = min(i0 + 1, p.h - 1);
         hrow(i0 - (ia - 1), ta, tal);
@@ -512,16 +523,17 @@ onepass_kernel(const __grid_constant__ CUtensorMap tmap, const OpParams p) {
             ++u;
         }
     }
+    const bool tail_row = xchg && ib < p.h;                          // exchange mode: row ib receives this tile's lower part
     while (u < ib) {
         do_group(u, ta, tal, tb, tbl, accA, accAl, accB, accBl);
-        emit_row(u, accA, accAl);                                    // row u complete; accB now collects row u+1
+        emit_row(u, accA, accAl, xchg && u == ia && ia > 0);         // row u complete; accB now collects row u+1
         ++u;
-        if (u >= ib) break;
+        if (u >= ib) { if (tail_row) emit_row(u, accB, accBl, true); break; }
         hrow(min(u + 1, p.h - 1) - (ia - 1), ta, tal);               // ta: new bottom row
         do_group(u, tb, tbl, ta, tal, accB, accBl, accA, accAl);
-        emit_row(u, accB, accBl);
+        emit_row(u, accB, accBl, false);                             // u > ia here
         ++u;
-        if (u >= ib) break;
+        if (u >= ib) { if (tail_row) emit_row(u, accA, accAl, true); break; }
         hrow(min(u + 1, p.h - 1) - (ia - 1), tb, tbl);
     }
 
@@ -562,6 +574,12 @@ onepass_kernel(const __grid_constant__ CUtensorMap tmap, const OpParams p) {
 // ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
+// SF_NO_XCHG=1: recompute the halo row group instead of exchanging the boundary row (A/B measurement, tests)
+inline bool op_no_xchg() {
+    const char* e = std::getenv("SF_NO_XCHG");
+    return e && e[0] == '1';
+}
+
 template <typename LT, int C, int S, int TH, int MINB, int UNR, int MODE, bool OHEM, bool HIST>
 inline int op_launch(const OnepassArgs& a) {
     using G = OpGeom<LT, C, S, TH>;
@@ -594,6 +612,14 @@ inline int op_launch(const OnepassArgs& a) {
         Workspace* w = reinterpret_cast<Workspace*>(a.ws);
         cudaError_t e = cudaMemsetAsync(w->fx_loss, 0, offsetof(Workspace, pad1) - offsetof(Workspace, fx_loss), st);
         if (e != cudaSuccess) return (int)e;
+        // Exchange mode: the first row of every tile is shared with the tile above (two atomic addends on a zeroed element).
+        // With h a multiple of TH those rows are every TH-th row of the whole [B*C*h][w] array: one strided memset.
+        p.xchg = p.tiles_y > 1 && a.h % TH == 0 && !op_no_xchg();
+        if (p.xchg) {
+            e = cudaMemset2DAsync(a.grad_acc, (size_t)TH * a.w * sizeof(float), 0, (size_t)a.w * sizeof(float),
+                                  (size_t)a.B * a.C * (a.h / TH), st);
+            if (e != cudaSuccess) return (int)e;
+        }
     }
     k<<<grid, kOpThreads, smem, st>>>(tmap, p);
     return (int)cudaGetLastError();
