@@ -235,3 +235,18 @@ def test_branch_hint_switches_route_without_changing_results(sf, monkeypatch):
     torch.cuda.synchronize()
     assert fn._BranchHint.last_branch(torch.device("cuda", torch.cuda.current_device())) == 1
     fn._BranchHint._by_device.clear()
+
+
+def test_onepass_boundary_row_exchange_matches_halo_recompute(sf, monkeypatch):
+    """Tiles hand the lower part of their last row group to the tile below through two float atomics on a zeroed row
+    (h a multiple of the tile height); SF_NO_XCHG=1 recomputes that row group in the lower tile instead.  Same loss and matrix,
+    gradients equal to rounding, and the exchange itself is bitwise reproducible."""
+    low, lab = _synth(61, 2, 19, 64, 128, 256, 512, "early", blk=16)          # 8-row tiles: 8 boundary rows per plane
+    l1, g1, h1 = _run(sf, low, lab, None, THR)
+    l1b, g1b, _ = _run(sf, low, lab, None, THR)
+    monkeypatch.setenv("SF_NO_XCHG", "1")
+    l2, g2, h2 = _run(sf, low, lab, None, THR)
+    assert torch.equal(g1, g1b) and l1.item() == l1b.item()
+    assert l1.item() == l2.item() and torch.equal(h1, h2)
+    assert (g1 - g2).abs().max().item() <= 1e-6 * g2.abs().max().item()
+    assert not torch.equal(g1, torch.zeros_like(g1))
