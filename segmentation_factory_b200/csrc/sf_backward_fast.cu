@@ -41,6 +41,7 @@ struct BfParams {
     int B, h, w, H, W, ignore, label_u8;
     int tiles_x, tiles_y;
     int Ctot, n_chunks;                         // chunked mode: classes in the tensor, CTAs per tile along channels
+    int xchg;                                   // fp32 gradients: boundary rows exchanged (two float atomics on zeroed rows)
 };
 
 template <typename LT, int C, int S>
@@ -139,7 +140,13 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
     const float2 l2e2 = splat(kLog2e);
 
     // ---- row walk state ----
-    const int Ya = TP::first(ia - 1 < -1 ? -1 : ia - 1);
+    // First group walked.  Halo mode: ia - 1, recomputed only for its lower vertical part into row ia.  Exchange mode (fp32
+    // gradients, p.xchg): ia -- the tile above adds its lower part of row ia itself and this tile adds its own into row ib;
+    // such a row has exactly two addends on a zeroed element, so the float atomics commute (sf_onepass.cuh does the same).
+    constexpr bool CAN_X = sizeof(LT) == 4;
+    const bool xchg = CAN_X && p.xchg != 0;
+    const int u0 = (xchg && ia > 0) ? ia : ia - 1;
+    const int Ya = TP::first(u0 < -1 ? -1 : u0);
     const int Yb = ib >= p.h ? p.H : TP::first(ib);                // exclusive
     // Prefetched inputs of the next row through running 64-bit pointers (base + 64-bit offset made ptxas rematerialise the
     // address products in the row loop); no guard around the loads -- the pointers stop at the tile's last row, which is then
@@ -207,7 +214,7 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
 
     int ecount = 0;
     // emit the finished source row i held in `acc`, then clear it.  Called uniformly by all threads.
-    auto emit_row = [&](int i, float2 (&acc)[NPA], float& accl) {
+    auto emit_row = [&](int i, float2 (&acc)[NPA], float& accl, bool shared_row) {
         if (i >= ia) {
             float* buf = Rbuf + (ecount & 1) * C * kBfThreads;
             ++ecount;
@@ -241,7 +248,8 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
                             sum = fmaf(v.x, wgt[d4], sum); sum = fmaf(v.y, wgt[d4 + 1], sum);
                             sum = fmaf(v.z, wgt[d4 + 2], sum); sum = fmaf(v.w, wgt[d4 + 3], sum);
                         }
-                        Logit<LT>::st(g + (long long)k * G::KQ * p.h * p.w, sum);
+                        if (CAN_X && shared_row) atomicAdd(reinterpret_cast<float*>(g + (long long)k * G::KQ * p.h * p.w), sum);
+                        else Logit<LT>::st(g + (long long)k * G::KQ * p.h * p.w, sum);
                     }
                 }
             }
@@ -321,8 +329,8 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
     __syncthreads();
     mbar_wait(bar, 0);
 
-    // ---- walk groups u = ia-1 .. ib-1, two per iteration with swapped roles (no register copies) ----
-    int u = ia - 1;
+    // ---- walk groups u = u0 .. ib-1, two per iteration with swapped roles (no register copies) ----
+    int u = u0;
     {
         const int i0 = max(u, 0), i1 = min(i0 + 1, p.h - 1);
         hrow(i0 - (ia - 1), ta, tal);
@@ -342,16 +350,17 @@ bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const BfParams p) {
         for (int q = 0; q < NP; ++q) chk += (ta[q].x + ta[q].y) + (tb[q].x + tb[q].y);
         if (chk == -1.2345678e38f) *reinterpret_cast<volatile float*>(smem) = chk;
     }
+    const bool tail_row = xchg && ib < p.h;                          // exchange mode: row ib receives this tile's lower part
     while (u < ib) {
         do_group(u, ta, tal, tb, tbl, accA, accAl, accB, accBl);
-        emit_row(u, accA, accAl);                                    // row u complete; accB now collects row u+1
+        emit_row(u, accA, accAl, xchg && u == ia && ia > 0);         // row u complete; accB now collects row u+1
         ++u;
-        if (u >= ib) break;
+        if (u >= ib) { if (tail_row) emit_row(u, accB, accBl, true); break; }
         hrow(min(u + 1, p.h - 1) - (ia - 1), ta, tal);               // ta: new bottom row
         do_group(u, tb, tbl, ta, tal, accB, accBl, accA, accAl);
-        emit_row(u, accB, accBl);
+        emit_row(u, accB, accBl, false);
         ++u;
-        if (u >= ib) break;
+        if (u >= ib) { if (tail_row) emit_row(u, accA, accAl, true); break; }
         hrow(min(u + 1, p.h - 1) - (ia - 1), tb, tbl);
     }
 }
@@ -383,7 +392,15 @@ static int bf_launch_d(const BwdArgs& a) {
     static SmemLimitOnce smem_once;                                  // per instantiation
     cudaError_t e = set_smem_limit_once(k, smem, smem_once);
     if (e != cudaSuccess) return (int)e;
-    k<<<(int)grid, kBfThreads, smem, reinterpret_cast<cudaStream_t>(a.stream)>>>(tmap, p);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(a.stream);
+    if (sizeof(LT) == 4 && p.tiles_y > 1 && a.h % kBfTH == 0 && !env_no_xchg()) {
+        // with h a multiple of the tile height the shared rows are every kBfTH-th row of the whole [B*C*h][w] array
+        p.xchg = 1;
+        e = cudaMemset2DAsync(a.grad_logits, (size_t)kBfTH * a.w * sizeof(float), 0, (size_t)a.w * sizeof(float),
+                              (size_t)a.B * a.C * (a.h / kBfTH), st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    k<<<(int)grid, kBfThreads, smem, st>>>(tmap, p);
     return (int)cudaGetLastError();
 }
 

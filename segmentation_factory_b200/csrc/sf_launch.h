@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 
+#include <cstdlib>
+
 #include <algorithm>
 
 namespace sf {
@@ -122,6 +124,12 @@ inline cudaError_t set_smem_limit_once(K kernel, size_t smem, SmemLimitOnce& slo
     const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) have = (int)smem;
     return e;
+}
+// SF_NO_XCHG=1 (read per launch): the gather-form kernels recompute the halo row group of a tile instead of exchanging the
+// boundary row with the tile above through two float atomics (A/B measurement, tests)
+inline bool env_no_xchg() {
+    const char* e = std::getenv("SF_NO_XCHG");
+    return e && e[0] == '1';
 }
 bool env_no_tma();
 bool env_no_fast();   // SF_NO_FAST=1: always take the generic kernels (A/B measurement, tests)

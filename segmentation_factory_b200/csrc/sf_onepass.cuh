@@ -574,12 +574,6 @@ onepass_kernel(const __grid_constant__ CUtensorMap tmap, const OpParams p) {
 // ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
-// SF_NO_XCHG=1: recompute the halo row group instead of exchanging the boundary row (A/B measurement, tests)
-inline bool op_no_xchg() {
-    const char* e = std::getenv("SF_NO_XCHG");
-    return e && e[0] == '1';
-}
-
 template <typename LT, int C, int S, int TH, int MINB, int UNR, int MODE, bool OHEM, bool HIST>
 inline int op_launch(const OnepassArgs& a) {
     using G = OpGeom<LT, C, S, TH>;
@@ -614,7 +608,7 @@ inline int op_launch(const OnepassArgs& a) {
         if (e != cudaSuccess) return (int)e;
         // Exchange mode: the first row of every tile is shared with the tile above (two atomic addends on a zeroed element).
         // With h a multiple of TH those rows are every TH-th row of the whole [B*C*h][w] array: one strided memset.
-        p.xchg = p.tiles_y > 1 && a.h % TH == 0 && !op_no_xchg();
+        p.xchg = p.tiles_y > 1 && a.h % TH == 0 && !env_no_xchg();
         if (p.xchg) {
             e = cudaMemset2DAsync(a.grad_acc, (size_t)TH * a.w * sizeof(float), 0, (size_t)a.w * sizeof(float),
                                   (size_t)a.B * a.C * (a.h / TH), st);
