@@ -19,6 +19,8 @@ def run(B, C, h, w, H, W, dtype=torch.float32, kind="ohem", late=False):
     loss = sf.fused_cross_entropy(x, lab.cuda(), None, 255, thr, hist)
     loss.backward()
     sf.eval_hist(x.detach(), lab.cuda(), 255, hist)
+    met, conf = sf.Metrics(C, 255, "cuda"), sf.ConfusionMatrix(C)
+    sf.fused_eval_update(x.detach(), lab.cuda(), met, conf)       # sf_eval_update: last-CTA accumulation where the fast kernel runs
     f = sf.FocalLoss(0.25, 2.0)(x, lab.cuda()); f.backward()
     d = sf.criterion(x, lab.cuda(), None, num_classes=C, dice=True, ignore_index=255); d.backward()   # dice walks + backward
     raw = torch.randint(0, 35, (B, H, W), generator=g, dtype=torch.uint8).cuda()

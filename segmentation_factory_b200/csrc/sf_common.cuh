@@ -190,6 +190,12 @@ __device__ __forceinline__ float lg2_approx(float x) {
 __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
+// shared-memory `*p += v` when `on`, as ONE predicated instruction (no branch / reconvergence point in the row loop)
+__device__ __forceinline__ void red_shared_add_if(uint32_t saddr, int v, bool on) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q red.shared.add.u32 [%0], %1;\n\t}"
+                 :: "r"(saddr), "r"(v), "r"((int)on) : "memory");
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -78,7 +78,10 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
     const int tid = threadIdx.x;
     const int tx = tid % kFfTW, sy = tid / kFfTW;
     if (tid < 32) cw_s[tid] = (p.class_w && tid < C) ? __ldg(p.class_w + tid) : 1.0f;
-    const bool want_hist = !DICE && !CSTAT && !NOHIST && p.hist != nullptr;
+    // FF_ARGMAX exists only to fill the matrix (sf_eval_hist refuses a null one): a compile-time `true` there keeps the
+    // per-row test of a kernel parameter (LDCU + 2 UISETP + BRA.U) out of the eval-only row loop
+    const bool want_hist = MODE == FF_ARGMAX ? true : (!DICE && !CSTAT && !NOHIST && p.hist != nullptr);
+    const uint32_t hist_sa = smem_u32(hist_s);
     const DiceBins bins{reinterpret_cast<unsigned*>(hist_s), C};                        // DSTAT: in the histogram area
     float* tab_s = reinterpret_cast<float*>(full + kFfStages);                          // DCOEF: ta[B][CP], tb[B][CP]
     const int lane = tid & 31;
@@ -234,13 +237,18 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
             long long px = ((long long)b * p.H + TP::first(u)) * p.W + X;
             float nanflag = 0.f;
             if (!SOFTMAX) {
+                // x * 0 is NaN exactly for NaN and Inf: packed probe over the group's lerped rows (two FFMA2 per channel pair)
+                float2 nan2 = make_float2(0.f, 0.f);
+                const float2 zero2 = make_float2(0.f, 0.f);
                 #pragma unroll
-                for (int q = 0; q < NP; ++q) nanflag = __fmaf_rn(bot[q].x + bot[q].y, 0.f, __fmaf_rn(top[q].x + top[q].y, 0.f, nanflag));
+                for (int q = 0; q < NP; ++q) nan2 = __ffma2_rn(bot[q], zero2, __ffma2_rn(top[q], zero2, nan2));
+                nanflag = nan2.x + nan2.y;
                 if (G::ODD) nanflag = __fmaf_rn(botl, 0.f, __fmaf_rn(topl, 0.f, nanflag));
             }
+            float lh1 = u < 0 ? 0.0f : 0.5f / S;                     // (r + 0.5) / S, stepped by 1/S per row (exact in fp32)
+            const float lh1_step = u < 0 ? 0.0f : 1.0f / S;
             #pragma unroll 1
-            for (int r = 0; r < cnt; ++r, px += p.W, labs >>= 8) {
-                const float lh1 = u < 0 ? 0.0f : ((float)r + 0.5f) * (1.0f / S);
+            for (int r = 0; r < cnt; ++r, px += p.W, labs >>= 8, lh1 += lh1_step) {
                 const float lh0 = 1.0f - lh1;
                 const float2 lh0_2 = splat(lh0), lh1_2 = splat(lh1);
                 float2 z[NP > 0 ? NP : 1];
@@ -352,11 +360,10 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
                     // count is kept as a per-thread run and added to the shared matrix only when the cell changes
                     // (cheaper than a per-pixel __match_any_sync vote: no MATCH / FLO / POPC, and the adds are rarer)
                     const int key = (colok && valid) ? lab * C + idx : -1;
-                    if (key != run_key) {
-                        if (run_key >= 0) atomicAdd(&hist_s[run_key], run_cnt);
-                        run_key = key; run_cnt = 0;
-                    }
-                    ++run_cnt;
+                    const bool chg = key != run_key;                 // straight-line: one predicated shared-memory red, no branch
+                    red_shared_add_if(hist_sa + 4u * (uint32_t)max(run_key, 0), run_cnt, chg && run_key >= 0);
+                    run_cnt = chg ? 1 : run_cnt + 1;
+                    run_key = key;
                 }
             }
         };

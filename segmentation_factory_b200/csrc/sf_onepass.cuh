@@ -98,12 +98,6 @@ __device__ __forceinline__ void op_onehot_sub2(int y, float2 (&a0)[NPA], float& 
 #undef SF_CASE
 }
 
-// shared-memory `*p += v` when `on`, as ONE predicated instruction (no branch / reconvergence point in the row loop)
-__device__ __forceinline__ void red_shared_add_if(uint32_t saddr, int v, bool on) {
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q red.shared.add.u32 [%0], %1;\n\t}"
-                 :: "r"(saddr), "r"(v), "r"((int)on) : "memory");
-}
-
 __device__ __forceinline__ float rcp_approx(float x) {
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
