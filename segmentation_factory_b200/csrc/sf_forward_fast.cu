@@ -40,6 +40,11 @@ struct FfParams {
 
 enum { FF_ARGMAX = 0, FF_SOFTMAX = 1, FF_DICE_STATS = 2, FF_DICE_COEF = 3, FF_SOFTMAX_STATS = 4, FF_SOFTMAX_NOHIST = 5 };
 
+// S labels of one byte each: 32 bits are enough for S <= 4 (64-bit shifts / selects cost two instructions each)
+template <int S> struct FfLabPack { using type = unsigned long long; };
+template <> struct FfLabPack<4> { using type = unsigned int; };
+template <> struct FfLabPack<2> { using type = unsigned int; };
+
 template <typename LT, int C, int S>
 struct FfGeom {
     static constexpr int GPS = 16 / S >= 2 ? 16 / S : 2;            // 16 rows per strip (S=8: 2 groups)
@@ -182,28 +187,37 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
         // pair.  Raw 64-bit loads for the NEXT group are issued a whole group ahead and only decoded when needed.
         int raw[S];
         float lsn[DICE ? S : 1], lsc[DICE ? S : 1];                  // DICE: the stored lse travels with the labels
+        // A thread's groups are consecutive, so its label rows are too: one running pointer per tile instead of rebuilding the
+        // 64-bit pixel index per group and row (fetch_labels is always called with the group after the previous call's)
+        const int lab_shift = p.label_u8 ? 0 : 3;
+        const long long lab_stride = (long long)p.W << lab_shift;
+        long long pxn = ((long long)b * p.H + TP::first(u_first)) * p.W + X;           // pixel index of the next row to fetch
+        const char* labp = reinterpret_cast<const char*>(p.labels) + (pxn << lab_shift);
         auto fetch_labels = [&](int u) {
             #pragma unroll
             for (int r = 0; r < S; ++r) raw[r] = -1;
             if (u <= p.h - 1 && colok) {
-                const int y0 = TP::first(u), cnt = TP::count(u, p.h);
-                const long long base = ((long long)b * p.H + y0) * p.W + X;
+                const int cnt = TP::count(u, p.h);
                 #pragma unroll
                 for (int r = 0; r < S; ++r)
                     if (r < cnt) {
-                        raw[r] = ld_label_lo32(p.labels, p.label_u8, base + (long long)r * p.W);
-                        if (DICE) lsn[r] = __ldg(p.dice.lse_in + base + (long long)r * p.W);
+                        const char* q = labp + r * lab_stride;
+                        raw[r] = p.label_u8 ? (int)__ldg(reinterpret_cast<const unsigned char*>(q)) : __ldg(reinterpret_cast<const int*>(q));
+                        if (DICE) lsn[r] = __ldg(p.dice.lse_in + pxn + (long long)r * p.W);
                     }
+                labp += cnt * lab_stride;
+                if (DICE) pxn += (long long)cnt * p.W;
             }
         };
-        auto pack_labels = [&]() -> unsigned long long {
-            unsigned long long pk = 0;
+        using LabPack = typename FfLabPack<S>::type;
+        auto pack_labels = [&]() -> LabPack {
+            LabPack pk = 0;
             #pragma unroll
             for (int r = 0; r < S; ++r) {
                 if (DICE) lsc[r] = lsn[r];
                 const int y = raw[r];
                 const unsigned v = (y != p.ignore && y >= 0 && y < C) ? (unsigned)y : 255u;
-                pk |= (unsigned long long)v << (8 * r);
+                pk |= (LabPack)v << (8 * r);
             }
             return pk;
         };
@@ -229,7 +243,7 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
 
         // one row group: `top`/`bot` hold the horizontal lerps of source rows i0 / i1
         auto do_group = [&](int u, const float2 (&top)[NP > 0 ? NP : 1], float topl,
-                            const float2 (&bot)[NP > 0 ? NP : 1], float botl, unsigned long long labs) {
+                            const float2 (&bot)[NP > 0 ? NP : 1], float botl, typename FfLabPack<S>::type labs) {
             const int i0 = max(u, 0), i1 = min(i0 + 1, p.h - 1);
             const int cnt = TP::count(u, p.h);
             const int o0 = (i0 - ua) * G::BW, o1 = (i1 - ua) * G::BW;
@@ -370,7 +384,7 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
 
         // dice walks: p_k = 2^(z_k log2e - rn(lse log2e)) * pcf from the stored lse; no max / argmax / histogram
         auto do_group_dice = [&](int u, const float2 (&top)[NP > 0 ? NP : 1], float topl,
-                                 const float2 (&bot)[NP > 0 ? NP : 1], float botl, unsigned long long labs) {
+                                 const float2 (&bot)[NP > 0 ? NP : 1], float botl, typename FfLabPack<S>::type labs) {
             const int i0 = max(u, 0), i1 = min(i0 + 1, p.h - 1);
             const int cnt = TP::count(u, p.h);
             const int o0 = (i0 - ua) * G::BW, o1 = (i1 - ua) * G::BW;
@@ -430,7 +444,7 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
             }
         };
         auto group = [&](int u, const float2 (&top)[NP > 0 ? NP : 1], float topl,
-                         const float2 (&bot)[NP > 0 ? NP : 1], float botl, unsigned long long labs) {
+                         const float2 (&bot)[NP > 0 ? NP : 1], float botl, typename FfLabPack<S>::type labs) {
             if (DICE) do_group_dice(u, top, topl, bot, botl, labs); else do_group(u, top, topl, bot, botl, labs);
         };
 
@@ -443,7 +457,7 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
             hrow(i0 - ua, ta, tal);
             hrow(i1 - ua, tb, tbl);
             if (u < 0) {                                             // rim group u = -1 shares (row 0, row 1) with u = 0
-                const unsigned long long labs = pack_labels();
+                const LabPack labs = pack_labels();
                 fetch_labels(u + 1);
                 group(u, ta, tal, tb, tbl, labs);
                 ++u;
@@ -451,7 +465,7 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
         }
         while (u < u_end) {
             {
-                const unsigned long long labs = pack_labels();
+                const LabPack labs = pack_labels();
                 fetch_labels(u + 1 < u_end ? u + 1 : p.h);
                 group(u, ta, tal, tb, tbl, labs);
                 ++u;
@@ -460,7 +474,7 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
             {
                 const int i1 = min(u + 1, p.h - 1);
                 hrow(i1 - ua, ta, tal);                              // ta: new bottom row, tb: top row
-                const unsigned long long labs = pack_labels();
+                const LabPack labs = pack_labels();
                 fetch_labels(u + 1 < u_end ? u + 1 : p.h);
                 group(u, tb, tbl, ta, tal, labs);
                 ++u;
