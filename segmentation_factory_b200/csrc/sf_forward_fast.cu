@@ -21,6 +21,12 @@
 
 namespace sf {
 
+// Experiment knob.  Measured: 3 CTAs per SM (80 registers, 100-470 B of spills) is SLOWER for the eval-only mode -- 0.128 vs
+// 0.120 ms per 8 Cityscapes images -- so 2 (113 registers, no spills) ships.
+#ifndef SF_FF_ARGMAX_CTAS
+#define SF_FF_ARGMAX_CTAS 2
+#endif
+constexpr int kFfArgmaxCtas = SF_FF_ARGMAX_CTAS;                   // resident CTAs per SM of the eval-only (argmax + matrix) mode
 constexpr int kFfTW = 64, kFfStrips = 4, kFfThreads = kFfTW * kFfStrips, kFfStages = 2;
 
 struct FfParams {
@@ -61,7 +67,7 @@ struct FfGeom {
 // MODE: FF_ARGMAX / FF_SOFTMAX are the forward proper; FF_DICE_STATS / FF_DICE_COEF are the two dice walks of
 // sf_dice.cu (same tiles, staging and strip walk, different per-pixel body: softmax from the stored lse, no argmax).
 template <typename LT, int C, int S, int MODE>
-__global__ void __launch_bounds__(kFfThreads, 2)
+__global__ void __launch_bounds__(kFfThreads, (MODE == FF_ARGMAX && C <= 21) ? kFfArgmaxCtas : 2)
 fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
     using G = FfGeom<LT, C, S>;
     using TP = ScaleTap<S>;
@@ -373,7 +379,7 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
                     // (GT, prediction) cell of this pixel.  A column's consecutive pixels mostly fall in the same cell, so the
                     // count is kept as a per-thread run and added to the shared matrix only when the cell changes
                     // (cheaper than a per-pixel __match_any_sync vote: no MATCH / FLO / POPC, and the adds are rarer)
-                    const int key = (colok && valid) ? lab * C + idx : -1;
+                    const int key = valid ? lab * C + idx : -1;           // columns outside the image carry label 255 (fetch_labels)
                     const bool chg = key != run_key;                 // straight-line: one predicated shared-memory red, no branch
                     red_shared_add_if(hist_sa + 4u * (uint32_t)max(run_key, 0), run_cnt, chg && run_key >= 0);
                     run_cnt = chg ? 1 : run_cnt + 1;
@@ -576,7 +582,7 @@ static int ff_launch(const FwdArgs& a) {
     cudaError_t e = set_smem_limit_once(k, smem, smem_once);
     if (e != cudaSuccess) return (int)e;
     const char* gm = std::getenv("SF_DEBUG_CTAS_PER_SM");             // experiment knob (occupancy sensitivity)
-    const int per_sm = gm ? std::max(1, atoi(gm)) : 2;
+    const int per_sm = gm ? std::max(1, atoi(gm)) : ((MODE == FF_ARGMAX && C <= 21) ? kFfArgmaxCtas : 2);
     const int grid = (int)std::min<long long>(total, std::min(kMaxCtas, per_sm * sm_count()));
     k<<<grid, kFfThreads, smem, reinterpret_cast<cudaStream_t>(a.stream)>>>(tmap, p);
     const int lrc = (int)cudaGetLastError();
