@@ -196,6 +196,12 @@ __device__ __forceinline__ void red_shared_add_if(uint32_t saddr, int v, bool on
                  :: "r"(saddr), "r"(v), "r"((int)on) : "memory");
 }
 
+// NaN-propagating maximum of three (FMNMX3.NAN): unlike fmaxf, a NaN input makes the result NaN
+__device__ __forceinline__ float max3_nan(float a, float b, float c) {
+    float d;
+    asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

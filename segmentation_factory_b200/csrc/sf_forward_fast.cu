@@ -255,16 +255,6 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
             const int o0 = (i0 - ua) * G::BW, o1 = (i1 - ua) * G::BW;
             const int cj0 = j0 - jO, cj1 = j1 - jO;
             long long px = ((long long)b * p.H + TP::first(u)) * p.W + X;
-            float nanflag = 0.f;
-            if (!SOFTMAX) {
-                // x * 0 is NaN exactly for NaN and Inf: packed probe over the group's lerped rows (two FFMA2 per channel pair)
-                float2 nan2 = make_float2(0.f, 0.f);
-                const float2 zero2 = make_float2(0.f, 0.f);
-                #pragma unroll
-                for (int q = 0; q < NP; ++q) nan2 = __ffma2_rn(bot[q], zero2, __ffma2_rn(top[q], zero2, nan2));
-                nanflag = nan2.x + nan2.y;
-                if (G::ODD) nanflag = __fmaf_rn(botl, 0.f, __fmaf_rn(topl, 0.f, nanflag));
-            }
             float lh1 = u < 0 ? 0.0f : 0.5f / S;                     // (r + 0.5) / S, stepped by 1/S per row (exact in fp32)
             const float lh1_step = u < 0 ? 0.0f : 1.0f / S;
             #pragma unroll 1
@@ -277,9 +267,11 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
                 for (int q = 0; q < NP; ++q) z[q] = rnd2<LT>(lerp2_pinned(top[q], lh0_2, bot[q], lh1_2));
                 if (G::ODD) zl = Logit<LT>::rnd(lerp_pinned(topl, lh0, botl, lh1));
                 // max as a 3-input tree (FMNMX3), then the lowest index that attains it (first-max rule of torch.argmax)
+                // Without the softmax (whose sum turns NaN by itself) the maximum is taken NaN-propagating (FMNMX3.NAN): a NaN
+                // among the channels then shows up in m and sends the pixel to the exact path below, as do +-0 and +-Inf maxima
                 float m = G::ODD ? zl : z[NP - 1].y;
                 #pragma unroll
-                for (int q = 0; q < NP; ++q) m = fmaxf(m, fmaxf(z[q].x, z[q].y));
+                for (int q = 0; q < NP; ++q) m = SOFTMAX ? fmaxf(m, fmaxf(z[q].x, z[q].y)) : max3_nan(m, z[q].x, z[q].y);
                 // First index attaining the maximum without a compare/select chain (2 ALU-pipe ops per channel, the pipe this
                 // kernel saturates): d_k = z_k - m is +0 exactly at the maximum and has its sign bit set elsewhere, so one funnel
                 // shift per channel collects the "below the maximum" bits and the index is the lowest clear bit.  +-0 maxima
@@ -320,7 +312,7 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
                         if (CSTAT) zl = exl;
                     }
                 }
-                const bool weird = (SOFTMAX ? (ssum != ssum) : (nanflag != nanflag)) || m == 0.f;
+                const bool weird = SOFTMAX ? ((ssum != ssum) || m == 0.f) : !(fabsf(m) > 0.f && fabsf(m) < INFINITY);
                 if (weird && NEED_IDX) {                              // torch: NaN beats everything, first NaN wins; -0 == +0
                     idx = -1;
                     int first_eq = C - 1;

@@ -321,3 +321,28 @@ def test_c_abi_direct_call(sf):
     rc = L.sf_ce_forward(x.data_ptr(), 0, y.data_ptr(), 0, 1, 19, 32, 64, 128, 256, 255, None, ctypes.c_float(-1.0),
                          None, None, None, ws.data_ptr(), 16, st)
     assert rc == -4 and b"workspace" in L.sf_strerror(rc)
+
+
+@pytest.mark.parametrize("C,dtype", [(19, torch.float32), (21, torch.bfloat16), (2, torch.float32), (9, torch.float16)])
+def test_eval_kernel_special_values_follow_torch_argmax(sf, C, dtype):
+    """The eval-only kernel takes its maximum NaN-propagating and sends NaN / +-Inf / +-0 maxima to an exact path: first NaN
+    wins, -0 == +0 (lowest index), ties go to the lowest index, -inf never wins, an all -inf pixel gives index 0."""
+    from oracle import torch_restatement as tr
+    low, lab = _synth(71, 1, C, 32, 64, 128, 256, "early")
+    low = ((low * 2).round() / 2).to(dtype).float()                           # ties; values exactly representable in `dtype`
+    low[0, C - 1, 10, 20] = float("nan")
+    low[0, 0, 10, 21] = float("nan")
+    low[0, 1, 10, 21] = float("nan")
+    low[0, 1, 3, 3] = float("inf")
+    low[0, 0, 20, 40] = float("-inf")
+    low[0, :, 22:24, 50:52] = float("-inf")                                   # every class -inf: NaN after interpolation or -inf
+    low[0, :, 25:30, 10:30] = 0.0                                             # every class ties at +0
+    low[0, C // 2, 25:30, 10:30] = -0.0
+    low[0, :, 16:20, 40:60] = -1.0
+    low[0, C - 1, 16:20, 40:60] = -0.0                                        # maximum is -0 ...
+    low[0, 0, 16:20, 44:48] = 0.0                                             # ... and +0 at a lower index in part of the area
+    x = low.to(dtype)
+    hist = torch.zeros(C, C, dtype=torch.int64, device="cuda")
+    sf.eval_hist(x.cuda(), lab.cuda(), 255, hist)
+    ref = tr.confusion_counts(tr.upsample(x, (128, 256)), lab, C)
+    assert torch.equal(hist.cpu(), ref)
