@@ -81,7 +81,7 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
     constexpr int CP = C + (C & 1);                                 // even pitch of the per-image dice tables (LDS.64 pairs)
     extern __shared__ __align__(128) unsigned char smem[];
     int* hist_s = reinterpret_cast<int*>(smem + kFfStages * G::STAGE_BYTES);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kFfStages * G::STAGE_BYTES + round_up(C * C * 4, 16));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kFfStages * G::STAGE_BYTES + round_up((C + 2) * C * 4, 16));
     __shared__ double red_scratch[kFfThreads / 32];
     __shared__ uint64_t empty_bar[kFfStages];                       // consumer -> producer: "every warp is done with this stage"
     __shared__ float cw_s[32];                                      // class weights as LDS: an LDG in the row loop would share
@@ -98,7 +98,7 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
     const int lane = tid & 31;
 
     if (want_hist)
-        for (int k = tid; k < C * C; k += kFfThreads) hist_s[k] = 0;
+        for (int k = tid; k < (C + 2) * C; k += kFfThreads) hist_s[k] = 0;   // row C collects the pixels that are not counted (row C + 1: slack)
     if (ACCP) bins.zero(tid, kFfThreads);
     if (DCOEF)
         for (int k = tid; k < 2 * p.B * CP; k += kFfThreads) {
@@ -131,7 +131,7 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
     double acc_loss = 0.0, acc_w = 0.0, acc_hard = 0.0;
     unsigned int cnt_valid = 0, cnt_hard = 0;
     const float2 l2e2 = splat(kLog2e);
-    int run_key = -1, run_cnt = 0;                                  // confusion-matrix run of this thread's column
+    int run_key = C * C, run_cnt = 0;                               // confusion-matrix run of this thread's column (starts in the spare row)
 
     // ---- dice state: sum p_k of this thread's roi pixels (DSTAT), flushed as integers so the result is order-free ----
     float2 accp[(ACCP && NP > 0) ? NP : 1];
@@ -371,9 +371,11 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
                     // (GT, prediction) cell of this pixel.  A column's consecutive pixels mostly fall in the same cell, so the
                     // count is kept as a per-thread run and added to the shared matrix only when the cell changes
                     // (cheaper than a per-pixel __match_any_sync vote: no MATCH / FLO / POPC, and the adds are rarer)
-                    const int key = valid ? lab * C + idx : -1;           // columns outside the image carry label 255 (fetch_labels)
+                    // not-counted pixels (label byte 255: ignored, out of range, outside the image) go to the spare row C of
+                    // the shared matrix, so the run needs no validity select and no "is there a run" guard
+                    const int key = min(lab, C) * C + idx;
                     const bool chg = key != run_key;                 // straight-line: one predicated shared-memory red, no branch
-                    red_shared_add_if(hist_sa + 4u * (uint32_t)max(run_key, 0), run_cnt, chg && run_key >= 0);
+                    red_shared_add_if(hist_sa + 4u * (uint32_t)run_key, run_cnt, chg);
                     run_cnt = chg ? 1 : run_cnt + 1;
                     run_key = key;
                 }
@@ -501,7 +503,7 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
         if (cur_b >= 0) flush_bins(cur_b);
     }
     if (want_hist) {
-        if (run_key >= 0) atomicAdd(&hist_s[run_key], run_cnt);
+        atomicAdd(&hist_s[run_key], run_cnt);
         __syncthreads();
         for (int k = tid; k < C * C; k += kFfThreads) {
             const int v = hist_s[k];
@@ -564,7 +566,7 @@ static int ff_launch(const FwdArgs& a) {
     CUtensorMap tmap{};
     const int rc = make_logits_tmap(&tmap, a.logits, a.ldtype, a.B * C, a.h, a.w, C, G::BH, G::BW);
     if (rc != 0) return rc;
-    size_t smem = (size_t)kFfStages * G::STAGE_BYTES + round_up(C * C * 4, 16) + kFfStages * 8 + 16;
+    size_t smem = (size_t)kFfStages * G::STAGE_BYTES + round_up((C + 2) * C * 4, 16) + kFfStages * 8 + 16;
     if (MODE == FF_DICE_COEF) {
         if ((long long)a.B * (C + 1) > 4096) return -1000;           // per-image tables live in shared memory
         smem += (size_t)2 * a.B * (C + (C & 1)) * 4;
