@@ -92,7 +92,9 @@ fwd_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FfParams p) {
     // FF_ARGMAX exists only to fill the matrix (sf_eval_hist refuses a null one): a compile-time `true` there keeps the
     // per-row test of a kernel parameter (LDCU + 2 UISETP + BRA.U) out of the eval-only row loop
     const bool want_hist = MODE == FF_ARGMAX ? true : (!DICE && !CSTAT && !NOHIST && p.hist != nullptr);
-    const uint32_t hist_sa = smem_u32(hist_s);
+    uint32_t hist_sa = smem_u32(hist_s);
+    asm volatile("mov.b32 %0, %0;" : "+r"(hist_sa));               // opaque: keeps the shared-window address in a register instead of
+                                                                    // rebuilding it (S2UR + UMOV + UIADD3 + ULEA) in every row
     const DiceBins bins{reinterpret_cast<unsigned*>(hist_s), C};                        // DSTAT: in the histogram area
     float* tab_s = reinterpret_cast<float*>(full + kFfStages);                          // DCOEF: ta[B][CP], tb[B][CP]
     const int lane = tid & 31;

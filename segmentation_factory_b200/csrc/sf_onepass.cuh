@@ -191,7 +191,8 @@ onepass_kernel(const __grid_constant__ CUtensorMap tmap, const OpParams p) {
     // grid = (tiles_x, tiles_y, B): tile coordinates come straight from the block index, so everything derived from them
     // (row range, base pointers of the label / loss streams) stays in uniform registers
     const int tid = threadIdx.x;
-    const uint32_t hist_sa = smem_u32(hist_s);                      // shared-window address, converted once
+    uint32_t hist_sa = smem_u32(hist_s);                            // shared-window address, converted once:
+    asm volatile("mov.b32 %0, %0;" : "+r"(hist_sa));               // opaque, or ptxas rebuilds it (4 uniform instructions) per row
     const int txi = blockIdx.x, tyi = blockIdx.y, b = blockIdx.z;
     const int ia = tyi * TH, ib = min(ia + TH, p.h);
     const int ja = txi * G::TBW, jb = min(ja + G::TBW, p.w);
