@@ -72,7 +72,7 @@ struct OpGeom {
     static constexpr int SRC_BYTES = round_up(C * PLANE * (int)sizeof(LT), 128);
     static constexpr int NP = C / 2;
     static constexpr bool ODD = (C & 1) != 0;
-    static constexpr int HIST_BYTES = round_up(C * C * 4, 16);
+    static constexpr int HIST_BYTES = round_up((C + 2) * C * 4, 16);   // C x C matrix + the spare row of not-counted pixels (+ slack)
     static constexpr int ROWS = S * TH + S;                         // label rows a tile walks (at most)
     static constexpr size_t smem(bool hist) {
         return (size_t)SRC_BYTES + (size_t)2 * C * kOpThreads * 4 + (hist ? HIST_BYTES : 0) + 16;
@@ -199,7 +199,7 @@ onepass_kernel(const __grid_constant__ CUtensorMap tmap, const OpParams p) {
     const int jO = (ja - 1) & ~(G::XAL - 1);                        // box x-origin: 16-byte aligned, -XAL for the first tile
     if (tid < 32) cw_s[tid] = (p.class_w && tid < C) ? __ldg(p.class_w + tid) : 1.0f;
     if (HIST)
-        for (int k = tid; k < C * C; k += kOpThreads) hist_s[k] = 0;
+        for (int k = tid; k < (C + 2) * C; k += kOpThreads) hist_s[k] = 0;
     if (tid == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
@@ -347,7 +347,7 @@ onepass_kernel(const __grid_constant__ CUtensorMap tmap, const OpParams p) {
     // per-thread loss statistics of the owned pixels (FUSED).  OHEM needs {n_valid, n_hard, sum_hard}; CE {n_valid, sum, sum_w}.
     float stat_a = 0.f, stat_b = 0.f;                               // OHEM: sum_hard, -        CE: sum_loss, sum_w
     int cnts = 0;                                                   // n_valid | n_hard << 16 of this tile's owned pixels (<= 68 rows)
-    int hrun_key = -1, hrun_cnt = 0;                                // confusion-matrix run of this thread's column
+    int hrun_key = C * C, hrun_cnt = 0;                             // confusion-matrix run of this thread's column (starts in the spare row)
 
     // one row group u: top/bot = lerped logits of rows i0/i1, at/ab = gradient accumulators of rows i0/i1
     auto do_group = [&](int u, const float2 (&top)[NPA], float topl, const float2 (&bot)[NPA], float botl,
@@ -462,12 +462,12 @@ onepass_kernel(const __grid_constant__ CUtensorMap tmap, const OpParams p) {
                                 }
                                 if (idx < 0) idx = first_eq;
                             }
-                            // run of (GT, prediction) cells down this column; halo lanes (not own) leave the run untouched
-                            int key = valid ? lo * C + idx : -1;
-                            key = own ? key : hrun_key;
+                            // run of (GT, prediction) cells down this column; pixels that are not counted (ignored or out-of-range
+                            // label, halo lanes) run into the spare row C of the shared matrix: no validity select, no run guard
+                            const int key = ((own && valid) ? lo : C) * C + idx;
                             const bool chg = key != hrun_key;
-                            red_shared_add_if(hist_sa + 4u * (uint32_t)max(hrun_key, 0), hrun_cnt, chg && hrun_key >= 0);
-                            hrun_cnt = chg ? 1 : hrun_cnt + (own ? 1 : 0);
+                            red_shared_add_if(hist_sa + 4u * (uint32_t)hrun_key, hrun_cnt, chg);
+                            hrun_cnt = chg ? 1 : hrun_cnt + 1;
                             hrun_key = key;
                         }
                     }
@@ -488,8 +488,10 @@ onepass_kernel(const __grid_constant__ CUtensorMap tmap, const OpParams p) {
                 }
             } else if (FUSED && HIST) {
                 // a row in which the whole warp is ignored still ends this column's matrix run
-                red_shared_add_if(hist_sa + 4u * (uint32_t)max(hrun_key, 0), hrun_cnt, own && hrun_key >= 0);
-                hrun_key = own ? -1 : hrun_key;
+                const bool chg = hrun_key != C * C;
+                red_shared_add_if(hist_sa + 4u * (uint32_t)hrun_key, hrun_cnt, chg);
+                hrun_cnt = chg ? 1 : hrun_cnt + 1;
+                hrun_key = C * C;
             }
             if (FUSED && OHEM) {
                 if (own) *lossp = l;
@@ -534,7 +536,7 @@ onepass_kernel(const __grid_constant__ CUtensorMap tmap, const OpParams p) {
 
     if (FUSED) {
         if (HIST) {
-            red_shared_add_if(hist_sa + 4u * (uint32_t)max(hrun_key, 0), hrun_cnt, hrun_key >= 0);
+            red_shared_add_if(hist_sa + 4u * (uint32_t)hrun_key, hrun_cnt, true);
             __syncthreads();
             for (int k = tid; k < C * C; k += kOpThreads) {
                 const int v = hist_s[k];
